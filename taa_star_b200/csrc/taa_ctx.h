@@ -1,0 +1,24 @@
+// taa_ctx.h — the context object behind the C-ABI (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "../../include/taa_b200.h"
+#include "taa_kernels.h"
+
+struct taa_ctx {
+	taa_desc desc{};
+	int num_sms = 0;
+	unsigned int* d_status = nullptr;  // device status word written by the kernels (halo overflow)
+	void* scratch[2] = {nullptr, nullptr};  // rgba16f out-res images for the unfused follow-on passes
+	long long launches = 0;            // kernels launched through this context
+	std::string last_error;
+};
+
+namespace taa {
+void set_error(taa_ctx* c, const char* fmt, ...);
+int cuda_fail(taa_ctx* c, cudaError_t e, const char* what);
+int build_resolve_args(taa_ctx* c, const taa_resolve_images* im, const TaaUniforms* u, ResolveArgs& A);
+int run_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s);
+// picks the kernel for this settings block: a tuned variant when one covers it, else the generic one
+cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s);
+}  // namespace taa

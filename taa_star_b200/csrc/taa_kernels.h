@@ -1,0 +1,17 @@
+// taa_kernels.h — host-callable launchers of the CUDA kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include "taa_device.cuh"
+
+namespace taa {
+
+// taa.comp, fully general, exact arithmetic (taa_resolve_generic.cu)
+cudaError_t launch_resolve_generic(const ResolveArgs& args, cudaStream_t stream);
+
+// follow-on passes, one kernel each as the reference dispatches them (taa_post.cu)
+struct PostImg { Img src; Img debug; ImgW dst; int w, h; };
+cudaError_t launch_sharpen(const PostImg& io, float sharpeningFactor, cudaStream_t stream);           // sharpen.comp
+cudaError_t launch_cas(const PostImg& io, const TaaCasPush& pc, cudaStream_t stream);                 // sharpen_cas.comp
+cudaError_t launch_post_process(const PostImg& io, const TaaPostProcessPush& pc, cudaStream_t stream); // post_process.comp
+
+}  // namespace taa

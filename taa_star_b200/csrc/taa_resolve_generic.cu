@@ -1,0 +1,471 @@
+// taa_resolve_generic.cu — the EXACT, fully general resolve kernel: every switch of `Parameters`
+// (shaders/taa.comp:50-95) is a warp-uniform runtime branch. One thread per output pixel.
+// It exists so that ANY settings block the reference accepts runs on the GPU; the tuned kernels in
+// taa_resolve_tuned.cu cover the BASELINE configs. Compiled with --fmad=false (see taa_device.cuh).
+#include "taa_device.cuh"
+#include "taa_kernels.h"
+
+namespace taa {
+
+namespace {
+
+struct Px {
+	const ResolveArgs& A;
+	const TaaParameters& P;
+	unsigned int* st;
+	__device__ Px(const ResolveArgs& a, const TaaParameters& p) : A(a), P(p), st(a.status) {}
+
+	// #define JITTER_UV (ubo.mJitterNdc.xy * 0.5 * params.mUnjitterFactor)           taa.comp:47
+	__device__ float2 jitter_uv() const {
+		return make_float2((A.ubo.mJitterNdc[0] * 0.5f) * P.mUnjitterFactor, (A.ubo.mJitterNdc[1] * 0.5f) * P.mUnjitterFactor);
+	}
+	__device__ f3 to_work_space(f3 rgb) const {  // maybe_rgb_to_ycocg(tonemap_rgb(.))   taa.comp:177,182
+		if (P.mToneMapLumaKaris) rgb = tonemap_karis(rgb);
+		return P.mUseYCoCg ? rgb_to_ycocg(rgb) : rgb;
+	}
+	__device__ float luminance(f3 c) const { return P.mUseYCoCg ? c.x : rgb_to_ycocg(c).x; }  // taa.comp:179
+
+	// one tap of getNeighbourhood / getCurrentColor                                  taa.comp:204-219
+	__device__ f3 colour_tap(float2 offset, int x, int y, float invw, float invh) const {
+		float s = offset.x + ((float)x + 0.5f) * invw;
+		float t = offset.y + ((float)y + 0.5f) * invh;
+		return to_work_space(xyz(tex_rgba16f(A.color, A.in_w, A.in_h, s, t, st)));
+	}
+
+	// getCurrentUpsampledColor                                                       taa.comp:222-257
+	__device__ f3 upsampled_colour(int cx, int cy, float& beta) const {
+		const float lox = (float)A.in_w, loy = (float)A.in_h, hix = (float)A.out_w, hiy = (float)A.out_h;
+		const float scx = hix / lox, scy = hiy / loy;
+		float2 j = jitter_uv();
+		const float tjx = (j.x * lox) * -1.0f, tjy = (j.y * loy) * -1.0f;
+		const float almostOne = 0.999999f;
+		float fx = -1.f, fy = -1.f;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			float px = (i & 1) ? almostOne : 0.f, py = (i & 2) ? almostOne : 0.f;
+			float sx = (floorf((lox * ((float)cx + px)) / hix) + 0.5f) + tjx;
+			float sy = (floorf((loy * ((float)cy + py)) / hiy) + 0.5f) + tjy;
+			if ((int)(sx * scx) == cx && (int)(sy * scy) == cy) { fx = sx; fy = sy; }
+		}
+		if (fx >= 0.0f) {
+			beta = 1.0f;
+			float s = (floorf(fx) + 0.5f) / lox, t = (floorf(fy) + 0.5f) / loy;
+			return to_work_space(xyz(tex_rgba16f(A.color, A.in_w, A.in_h, s, t, st)));
+		}
+		beta = 0.0f;
+		return mk3(0.f, 0.f, 0.f);
+	}
+
+	// findClosestUvAndZ_3x3                                                          taa.comp:371-389
+	__device__ float2 closest_uv_3x3(float u, float v) const {
+		const float tx = 1.0f / (float)A.in_w, ty = 1.0f / (float)A.in_h;
+		float cox = tx * -1.f, coy = ty * -1.f;
+		float dClosest = tex_r32f(A.depth, A.in_w, A.in_h, u + cox, v + coy, st);
+#pragma unroll
+		for (int i = 1; i < 9; ++i) {
+			float ox = tx * (float)(i % 3 - 1), oy = ty * (float)(i / 3 - 1);
+			float d = tex_r32f(A.depth, A.in_w, A.in_h, u + ox, v + oy, st);
+			if (d < dClosest) { cox = ox; coy = oy; dClosest = d; }
+		}
+		return make_float2(u + cox, v + coy);
+	}
+
+	// sample_history_rgba                                                            taa.comp:441-549
+	__device__ float4 hist(float s, float t) const { return tex_rgba16f(A.history_in, A.out_w, A.out_h, s, t, st); }
+	__device__ float4 sample_history(float u, float v) const {
+		if (P.mInterpolationMode == 0) return hist(u, v);
+		const float W = (float)A.out_w, H = (float)A.out_h;
+		const float iw = 1.0f / W, ih = 1.0f / H;
+		const float ix = u * W, iy = v * H;
+		const float tcx = floorf(ix - 0.5f) + 0.5f, tcy = floorf(iy - 0.5f) + 0.5f;
+		const float fx = ix - tcx, fy = iy - tcy;
+		const float fx2 = fx * fx, fy2 = fy * fy, fx3 = fx2 * fx, fy3 = fy2 * fy;
+		if (P.mInterpolationMode == 1) {  // b-spline, 4 bilinear taps                     taa.comp:517-543
+			float w0x = fx2 - 0.5f * (fx3 + fx), w0y = fy2 - 0.5f * (fy3 + fy);
+			float w1x = 1.5f * fx3 - 2.5f * fx2 + 1.0f, w1y = 1.5f * fy3 - 2.5f * fy2 + 1.0f;
+			float w3x = 0.5f * (fx3 - fx2), w3y = 0.5f * (fy3 - fy2);
+			float w2x = 1.0f - w0x - w1x - w3x, w2y = 1.0f - w0y - w1y - w3y;
+			float s0x = w0x + w1x, s0y = w0y + w1y, s1x = w2x + w3x, s1y = w2y + w3y;
+			float f0x = w1x / (w0x + w1x), f0y = w1y / (w0y + w1y);
+			float f1x = w3x / (w2x + w3x), f1y = w3y / (w2y + w3y);
+			float t0x = (tcx - 1.0f + f0x) * iw, t0y = (tcy - 1.0f + f0y) * ih;
+			float t1x = (tcx + 1.0f + f1x) * iw, t1y = (tcy + 1.0f + f1y) * ih;
+			return (hist(t0x, t0y) * s0x + hist(t1x, t0y) * s1x) * s0y + (hist(t0x, t1y) * s0x + hist(t1x, t1y) * s1x) * s1y;
+		}
+		// catmull-rom, 9 bilinear taps                                                   taa.comp:441-514
+		float w0x = -0.5f * fx3 + fx2 - 0.5f * fx, w0y = -0.5f * fy3 + fy2 - 0.5f * fy;
+		float w1x = 1.5f * fx3 - 2.5f * fx2 + 1.0f, w1y = 1.5f * fy3 - 2.5f * fy2 + 1.0f;
+		float w2x = -1.5f * fx3 + 2.0f * fx2 + 0.5f * fx, w2y = -1.5f * fy3 + 2.0f * fy2 + 0.5f * fy;
+		float w3x = 0.5f * fx3 - 0.5f * fx2, w3y = 0.5f * fy3 - 0.5f * fy2;
+		float wCx = w1x + w2x, wCy = w1y + w2y;
+		float t0x = (tcx - 1.0f) * iw, t0y = (tcy - 1.0f) * ih;
+		float tCx = (tcx + w2x / wCx) * iw, tCy = (tcy + w2y / wCy) * ih;
+		float t3x = (tcx + 2.0f) * iw, t3y = (tcy + 2.0f) * ih;
+		float4 r = hist(t0x, t0y) * w0x * w0y;
+		r = r + hist(tCx, t0y) * wCx * w0y;
+		r = r + hist(t3x, t0y) * w3x * w0y;
+		r = r + hist(t0x, tCy) * w0x * wCy;
+		r = r + hist(tCx, tCy) * wCx * wCy;
+		r = r + hist(t3x, tCy) * w3x * wCy;
+		r = r + hist(t0x, t3y) * w0x * w3y;
+		r = r + hist(tCx, t3y) * wCx * w3y;
+		r = r + hist(t3x, t3y) * w3x * w3y;
+		return r;
+	}
+
+	// ---- segmentation mask helpers                                                  taa.comp:559-587
+	__device__ float lin_depth(int x, int y) const {
+		float d = fetch_r32f(A.depth, A.in_w, A.in_h, x, y, st);
+		float n = A.ubo.mCamNearPlane, f = A.ubo.mCamFarPlane;
+		return n * f / (f + d * (n - f));
+	}
+	__device__ float luma_at(int x, int y) const { return rgb_to_ycocg(xyz(fetch_rgba16f(A.color, A.in_w, A.in_h, x, y, st))).x; }
+	__device__ f3 normal_at(int x, int y) const {
+		float4 n = fetch_rgba32f(A.uvnrm, A.in_w, A.in_h, x, y, st);
+		return mk3(cosf(n.z) * cosf(n.w), sinf(n.z) * cosf(n.w), sinf(n.w));
+	}
+	__device__ static float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+	template <class F>
+	__device__ float sobel_len(int x, int y, F f) const {
+		const int xl = iclamp(x - 1, 0, A.in_w - 1), xr = iclamp(x + 1, 0, A.in_w - 1), xc = iclamp(x, 0, A.in_w - 1);
+		const int yt = iclamp(y - 1, 0, A.in_h - 1), yb = iclamp(y + 1, 0, A.in_h - 1), yc = iclamp(y, 0, A.in_h - 1);
+		float c00 = f(xl, yt), c01 = f(xc, yt), c02 = f(xr, yt), c10 = f(xl, yc), c12 = f(xr, yc), c20 = f(xl, yb), c21 = f(xc, yb), c22 = f(xr, yb);
+		float gx = c00 - c20 + 2.0f * c01 - 2.0f * c21 + c02 - c22;
+		float gy = c00 - c02 + 2.0f * c10 - 2.0f * c12 + c20 - c22;
+		return sqrtf(gx * gx + gy * gy);
+	}
+	// calc_segmentation_value                                                        taa.comp:589-702
+	__device__ unsigned int segmentation(int x, int y, float hu, float hv) const {
+		const unsigned int flags = P.mRayTraceAugmentFlags;
+		if (flags & TAA_RTFLAG_FXD) {
+			const int b = 100;
+			if (x < b || y < b || x >= A.in_w - b || y >= A.in_h - b) return 1u;
+		}
+		if (flags & TAA_RTFLAG_ALL) return 2u;
+		const bool useCnt = (flags & TAA_RTFLAG_CNT) != 0;
+		const unsigned int newCnt = useCnt ? ((unsigned int)P.mRayTraceHistoryCount << 16) : 0u;
+		if (flags & TAA_RTFLAG_OUT) {
+			if (hu < 0.f || hv < 0.f || hu >= 1.f || hv >= 1.f) return 1u;
+		}
+		const unsigned int matId = fetch_r32ui(A.matid, A.in_w, A.in_h, x, y, st);
+		if (flags & TAA_RTFLAG_DIS) {
+			int px = (int)(hu * (float)A.in_w), py = (int)(hv * (float)A.in_h);
+			if (px >= 0 && py >= 0 && px < A.in_w && py < A.in_h) {
+				unsigned int prev = fetch_r32ui(A.prev_matid, A.in_w, A.in_h, px, py, st);
+				if (prev != matId && (prev & 0x80000000u)) return 2u | newCnt;
+			}
+		}
+		float nrm = 0.f, dpt = 0.f, mat = 0.f, lum = 0.f;
+		const int xl = iclamp(x - 1, 0, A.in_w - 1), xr = iclamp(x + 1, 0, A.in_w - 1), xc = iclamp(x, 0, A.in_w - 1);
+		const int yt = iclamp(y - 1, 0, A.in_h - 1), yb = iclamp(y + 1, 0, A.in_h - 1), yc = iclamp(y, 0, A.in_h - 1);
+		if (flags & TAA_RTFLAG_NRM) {
+			f3 nC = normal_at(x, y), nL = normal_at(xl, yc), nR = normal_at(xr, yc), nT = normal_at(xc, yt), nB = normal_at(xc, yb);
+			float mind = fmaxf(0.f, fminf(fminf(fminf(dot3(nC, nL), dot3(nC, nR)), dot3(nC, nT)), dot3(nC, nB)));
+			nrm = 1.0f - mind;
+		}
+		if (flags & TAA_RTFLAG_DPT) dpt = sobel_len(x, y, [&](int a, int b) { return lin_depth(a, b); });
+		if (flags & TAA_RTFLAG_MID) {
+			if (matId != fetch_r32ui(A.matid, A.in_w, A.in_h, xl, yc, st) || matId != fetch_r32ui(A.matid, A.in_w, A.in_h, xr, yc, st) ||
+			    matId != fetch_r32ui(A.matid, A.in_w, A.in_h, xc, yt, st) || matId != fetch_r32ui(A.matid, A.in_w, A.in_h, xc, yb, st))
+				mat = 1.0f;
+		}
+		if (flags & TAA_RTFLAG_LUM) lum = sobel_len(x, y, [&](int a, int b) { return luma_at(a, b); });
+		float total = nrm * P.mRayTraceAugment_WNrm + dpt * P.mRayTraceAugment_WDpt + mat * P.mRayTraceAugment_WMId + lum * P.mRayTraceAugment_WLum;
+		if (total >= P.mRayTraceAugment_Thresh) return 2u | newCnt;
+		if (useCnt) {
+			unsigned int oldCnt = (fetch_r32ui(A.prev_segmask, A.out_w, A.out_h, x, y, st) & 0xffff0000u) >> 16;
+			if (oldCnt > 0) return 2u | ((oldCnt - 1) << 16);
+		}
+		return 0u;
+	}
+};
+
+}  // namespace
+
+// main()                                                                              taa.comp:708-960
+__global__ void __launch_bounds__(256) taa_resolve_generic_kernel(const __grid_constant__ ResolveArgs A) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = A.band_y0 + blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= A.out_w || y >= A.band_y0 + A.band_rows || y >= A.out_h) return;
+	unsigned int* st = A.status;
+
+	const TaaParameters& P = A.ubo.param[(A.ubo.splitScreen && x > A.ubo.splitX) ? 1 : 0];
+	Px px(A, P);
+
+	const float u = ((float)x + 0.5f) / (float)A.out_w;  // tc_to_uv                       taa.comp:131
+	const float v = ((float)y + 0.5f) / (float)A.out_h;
+	const int lx = (int)(u * (float)A.in_w), ly = (int)(v * (float)A.in_h);  // uv_to_tc  taa.comp:724
+
+	if (P.mPassThrough) {  // taa.comp:726-731
+		float4 c = fetch_rgba16f(A.color, A.in_w, A.in_h, lx, ly, st);
+		float4 h = fetch_rgba16f(A.history_in, A.out_w, A.out_h, x, y, st);
+		st_rgba16f(A.result, x, y, make_float4(c.x, c.y, c.z, 1.f));
+		st_rgba16f(A.history_out, x, y, make_float4(h.x, h.y, h.z, 1.f));
+		st_rgba16f(A.debug, x, y, make_float4(0.f, 0.f, 0.f, 0.f));
+		st_r32ui(A.mask, x, y, 0u);
+		return;
+	}
+	if (A.ubo.mBypassHistoryUpdate) {  // taa.comp:732-737
+		float4 h = fetch_rgba16f(A.history_in, A.out_w, A.out_h, x, y, st);
+		st_rgba16f(A.result, x, y, make_float4(h.x, h.y, h.z, 1.f));
+		st_rgba16f(A.history_out, x, y, make_float4(h.x, h.y, h.z, 1.f));
+		st_rgba16f(A.debug, x, y, make_float4(0.f, 0.f, 0.f, 0.f));
+		st_r32ui(A.mask, x, y, 0u);
+		return;
+	}
+
+	// ---- getColorAndAabb                                                             taa.comp:259-319
+	const float invw = 1.0f / (float)A.in_w, invh = 1.0f / (float)A.in_h;
+	f3 colMin, colMax, clipTowards;
+	{
+		float2 off = P.mUnjitterNeighbourhood ? px.jitter_uv() : make_float2(0.f, 0.f);
+		f3 cC = px.colour_tap(off, lx, ly, invw, invh);
+		f3 c1 = px.colour_tap(off, lx - 1, ly - 1, invw, invh);
+		f3 c2 = px.colour_tap(off, lx, ly - 1, invw, invh);
+		f3 c3 = px.colour_tap(off, lx + 1, ly - 1, invw, invh);
+		f3 c4 = px.colour_tap(off, lx - 1, ly, invw, invh);
+		f3 c5 = px.colour_tap(off, lx + 1, ly, invw, invh);
+		f3 c6 = px.colour_tap(off, lx - 1, ly + 1, invw, invh);
+		f3 c7 = px.colour_tap(off, lx, ly + 1, invw, invh);
+		f3 c8 = px.colour_tap(off, lx + 1, ly + 1, invw, invh);
+		if (P.mVarianceClipping) {
+			const float N = 9.0f;
+			f3 m1 = cC + c1 + c2 + c3 + c4 + c5 + c6 + c7 + c8;
+			f3 m2 = cC * cC + c1 * c1 + c2 * c2 + c3 * c3 + c4 * c4 + c5 * c5 + c6 * c6 + c7 * c7 + c8 * c8;
+			f3 mean = m1 / N;
+			f3 var = max3(mk3(0.f, 0.f, 0.f), m2 / N - mean * mean);
+			f3 sigma = mk3(sqrtf(var.x), sqrtf(var.y), sqrtf(var.z));
+			colMin = mean - P.mVarClipGamma * sigma;
+			colMax = mean + P.mVarClipGamma * sigma;
+			clipTowards = mean;
+		} else if (P.mShapedNeighbourhood) {
+			f3 mn9 = min3(min3(min3(min3(min3(min3(min3(min3(cC, c1), c2), c3), c4), c5), c6), c7), c8);
+			f3 mx9 = max3(max3(max3(max3(max3(max3(max3(max3(cC, c1), c2), c3), c4), c5), c6), c7), c8);
+			f3 mn5 = min3(min3(min3(min3(cC, c2), c4), c5), c7);
+			f3 mx5 = max3(max3(max3(max3(cC, c2), c4), c5), c7);
+			colMin = (mn9 + mn5) * 0.5f;
+			colMax = (mx9 + mx5) * 0.5f;
+			clipTowards = cC;
+		} else {
+			colMin = min3(min3(min3(min3(min3(min3(min3(min3(cC, c1), c2), c3), c4), c5), c6), c7), c8);
+			colMax = max3(max3(max3(max3(max3(max3(max3(max3(cC, c1), c2), c3), c4), c5), c6), c7), c8);
+			clipTowards = cC;
+		}
+		if (P.mUseYCoCg && P.mShrinkChromaAxis) {
+			f3 halfSize = mk3(0.5f * 1.0f, 0.5f * 0.5f, 0.5f * 0.5f) * (colMax - colMin);
+			f3 center = (colMin + colMax) * 0.5f;
+			colMin = center - halfSize;
+			colMax = center + halfSize;
+			if (clipTowards.x < colMin.x || clipTowards.y < colMin.y || clipTowards.z < colMin.z ||
+			    clipTowards.x > colMax.x || clipTowards.y > colMax.y || clipTowards.z > colMax.z)
+				clipTowards = center;
+		}
+	}
+
+	// ---- current colour                                                              taa.comp:750-756
+	f3 cur;
+	float beta;
+	if (A.ubo.mUpsampling) {
+		cur = px.upsampled_colour(x, y, beta);
+	} else {
+		float2 off = P.mUnjitterCurrentSample ? px.jitter_uv() : make_float2(0.f, 0.f);
+		cur = px.colour_tap(off, lx, ly, invw, invh);
+		beta = 1.0f;
+	}
+	const float depth = fetch_r32f(A.depth, A.in_w, A.in_h, lx, ly, st);
+
+	// ---- getHistoryPosition                                                          taa.comp:391-438
+	float hu, hv, expectedHistoryDepth;
+	{
+		float4 vel = tex_rgba16f(A.velocity, A.in_w, A.in_h, u, v, st);
+		bool canUseVelocity = !(P.mUseVelocityVectors == 0 || (P.mUseVelocityVectors == 1 && vel.w < 0.5f));
+		if (canUseVelocity) {
+			if (P.mVelocitySampleMode == 1) {
+				const int ox[8] = {1, -1, -1, 0, -1, 0, 1, 1}, oy[8] = {-1, 0, -1, -1, 1, 1, 0, 1};
+				float mvx = vel.x, mvy = vel.y, sx = vel.x, sy = vel.y;
+#pragma unroll
+				for (int i = 0; i < 8; ++i) {
+					float4 s4 = tex_rgba16f(A.velocity, A.in_w, A.in_h, u + invw * (float)ox[i], v + invh * (float)oy[i], st);
+					sx = s4.x;
+					sy = s4.y;
+					if (sx * sx + sy * sy > mvx * mvx + mvy * mvy) { mvx = sx; mvy = sy; }
+				}
+				vel.x = sx;  // taa.comp:412 (sic)
+				vel.y = sy;
+			} else if (P.mVelocitySampleMode == 2) {
+				float2 c = px.closest_uv_3x3(u, v);
+				vel = tex_rgba16f(A.velocity, A.in_w, A.in_h, c.x, c.y, st);
+			}
+			hu = u - vel.x;
+			hv = v - vel.y;
+			expectedHistoryDepth = depth - vel.z;
+		} else {
+			const float* Mi = A.ubo.mInverseViewProjMatrix;
+			const float* Mh = A.ubo.mHistoryViewProjMatrix;
+			float cx = u * 2.0f - 1.0f, cy = v * 2.0f - 1.0f, cz = depth, cw = 1.0f;
+			float wx = ((Mi[0] * cx + Mi[4] * cy) + Mi[8] * cz) + Mi[12] * cw;
+			float wy = ((Mi[1] * cx + Mi[5] * cy) + Mi[9] * cz) + Mi[13] * cw;
+			float wz = ((Mi[2] * cx + Mi[6] * cy) + Mi[10] * cz) + Mi[14] * cw;
+			float ww = ((Mi[3] * cx + Mi[7] * cy) + Mi[11] * cz) + Mi[15] * cw;
+			float hx = ((Mh[0] * wx + Mh[4] * wy) + Mh[8] * wz) + Mh[12] * ww;
+			float hy = ((Mh[1] * wx + Mh[5] * wy) + Mh[9] * wz) + Mh[13] * ww;
+			float hz = ((Mh[2] * wx + Mh[6] * wy) + Mh[10] * wz) + Mh[14] * ww;
+			float hw = ((Mh[3] * wx + Mh[7] * wy) + Mh[11] * wz) + Mh[15] * ww;
+			hu = (hx / hw) * 0.5f + 0.5f;
+			hv = (hy / hw) * 0.5f + 0.5f;
+			expectedHistoryDepth = hz / hw;
+		}
+	}
+	const float du = u - hu, dv = v - hv;
+	const float pixelSpeed = sqrtf(du * du + dv * dv);
+
+	const float4 historyRaw = px.sample_history(hu, hv);
+	f3 hist = P.mUseYCoCg ? rgb_to_ycocg(xyz(historyRaw)) : xyz(historyRaw);
+
+	float alpha = P.mAlpha;
+	bool rejected = false;
+
+	unsigned int seg = 0u;
+	const bool genSeg = P.mRayTraceAugment != 0;
+	if (genSeg) {  // taa.comp:775-784
+		seg = px.segmentation(x, y, hu, hv);
+		if (seg & 3u) { alpha = P.mRejectionAlpha; rejected = true; }
+	}
+
+	// ---- history rejection                                                           taa.comp:787-823
+	if (P.mRejectOutside) {
+		if (hu < 0.f || hv < 0.f || hu >= 1.f || hv >= 1.f) { alpha = P.mRejectionAlpha; rejected = true; }
+	}
+	float writeDynamicMask = 0.f;
+	if (P.mDynamicAntiGhosting) {
+		const float eps = 1e-5f;
+		auto mov = [&](float s, float t) {
+			float4 q = tex_rgba16f(A.velocity, A.in_w, A.in_h, s, t, st);
+			return (fabsf(q.x) > eps || fabsf(q.y) > eps) && (fabsf(q.w) >= 0.5f);
+		};
+		bool movL = mov(u + invw * -1.f, v + invh * 0.f);
+		bool movR = mov(u + invw * 1.f, v + invh * 0.f);
+		bool movT = mov(u + invw * 0.f, v + invh * -1.f);
+		bool movB = mov(u + invw * 0.f, v + invh * 1.f);
+		bool movC = mov(u, v);
+		if (!(movL || movR || movT || movB || movC) && historyRaw.w > 0.0f) rejected = true;
+		writeDynamicMask = movC ? 1.0f : 0.0f;
+	}
+	if (P.mDepthCulling) {
+		int tx = (int)(hu * (float)A.in_w), ty = (int)(hv * (float)A.in_h);
+		float hd = fetch_r32f(A.history_depth, A.in_w, A.in_h, tx, ty, st);
+		float depthEpsilon = 0.1f * (1.0f - hd);
+		if (fabsf(hd - expectedHistoryDepth) > depthEpsilon) rejected = true;
+	}
+
+	// ---- rectification                                                               taa.comp:826-845
+	const f3 origHist = hist;
+	switch (P.mColorClampingOrClipping) {
+		case 1: hist = min3(max3(hist, colMin), colMax); break;
+		case 2: {  // clipAabb(colMin, colMax, vec4(0,0,0,1), vec4(hist,1))               taa.comp:323-345
+			const float eps = 1e-7f;
+			f3 pClip = 0.5f * (colMax + colMin);
+			f3 e = 0.5f * (colMax - colMin);
+			f3 eClip = mk3(e.x + eps, e.y + eps, e.z + eps);
+			f3 vClip = hist - pClip;
+			f3 aUnit = abs3(vClip / eClip);
+			float maUnit = fmaxf(aUnit.x, fmaxf(aUnit.y, aUnit.z));
+			if (maUnit > 1.0f) hist = pClip + vClip / maUnit;
+			break;
+		}
+		case 3: {  // clipAabbSlow(colMin, colMax, vec4(clipTowards,1), vec4(hist,1))     taa.comp:348-369
+			const float eps = 1e-7f;
+			f3 p = clipTowards;
+			f3 r = hist - p;
+			f3 rmax = colMax - p, rmin = colMin - p;
+			if (r.x > rmax.x + eps) r = r * (rmax.x / r.x);
+			if (r.y > rmax.y + eps) r = r * (rmax.y / r.y);
+			if (r.z > rmax.z + eps) r = r * (rmax.z / r.z);
+			if (r.x < rmin.x - eps) r = r * (rmin.x / r.x);
+			if (r.y < rmin.y - eps) r = r * (rmin.y / r.y);
+			if (r.z < rmin.z - eps) r = r * (rmin.z / r.z);
+			hist = p + r;
+			break;
+		}
+		default: break;
+	}
+	const f3 rdiff = hist - origHist;
+	const bool rectified = fabsf(rdiff.x) > 0.001f || fabsf(rdiff.y) > 0.001f || fabsf(rdiff.z) > 0.001f;
+
+	// ---- blending                                                                    taa.comp:848-900
+	if (rejected) {
+		alpha = P.mRejectionAlpha;
+		beta = 1.0f;
+	} else {
+		if (P.mVelBasedAlpha) alpha = fmaxf(alpha, mixf(alpha, P.mVelBasedAlphaMax, clampf(pixelSpeed * P.mVelBasedAlphaFactor, 0.f, 1.f)));
+		if (P.mLumaWeightingLottes) {
+			float lc = px.luminance(cur), lh = px.luminance(hist);
+			float diff = fabsf(lc - lh) / fmaxf(fmaxf(lc, lh), 0.2f);
+			float w = 1.0f - diff;
+			alpha = mixf(P.mMaxAlpha, P.mMinAlpha, w * w);
+		}
+		if (P.mReduceBlendNearClamp) {
+			float lmin = px.luminance(colMin), lmax = px.luminance(colMax), lh = px.luminance(origHist);
+			float distToClamp = 2.0f * fabsf(fminf(lh - lmin, lmax - lh)) / (lmax - lmin);
+			if (lmax - lmin < 0.001f) distToClamp = 1.0f;
+			alpha *= clampf(4.0f * distToClamp, 0.f, 1.f);
+		}
+	}
+	if (A.ubo.mResetHistory) { alpha = 1.0f; beta = 1.0f; }
+
+	const float ab = alpha * beta;
+	f3 aa = mk3(mixf(hist.x, cur.x, ab), mixf(hist.y, cur.y, ab), mixf(hist.z, cur.z, ab));
+	if (P.mUseYCoCg) aa = ycocg_to_rgb(aa);
+	if (P.mAddNoise) {  // noise()                                                        taa.comp:551-556
+		float sx = u + A.ubo.mSinTime[0] + 0.6959174f, sy = v + A.ubo.mSinTime[0] + 0.6959174f;
+		float s = sinf(sx * 12.9898f + sy * 78.233f);
+		float n0 = s * 43758.5453f, n1 = s * 28001.8384f, n2 = s * 50849.4141f;
+		n0 = n0 - floorf(n0); n1 = n1 - floorf(n1); n2 = n2 - floorf(n2);
+		aa.x = aa.x + (n0 * 2.0f - 1.0f) * P.mNoiseFactor;
+		aa.y = aa.y + (n1 * 2.0f - 1.0f) * P.mNoiseFactor;
+		aa.z = aa.z + (n2 * 2.0f - 1.0f) * P.mNoiseFactor;
+	}
+	const float4 toHistory = mk4(aa, writeDynamicMask);
+	const float4 toScreen = mk4(P.mToneMapLumaKaris ? un_tonemap_karis(aa) : aa, 1.0f);
+
+	st_rgba16f(A.history_out, x, y, toHistory);
+	st_rgba16f(A.result, x, y, toScreen);
+
+	if (A.debug.p) {  // taa.comp:912-942, 957
+		float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+		switch (P.mDebugMode) {
+			case 0: d = mk4(colMax - colMin, 0.f); break;
+			case 1: { f3 t = colMax - colMin; float q = t.x * t.y * t.z; d = make_float4(q, q, q, 0.f); break; }
+			case 2: d = make_float4(rejected ? 1.f : 0.f, sqrtf(rdiff.x * rdiff.x + rdiff.y * rdiff.y + rdiff.z * rdiff.z), 0.f, 0.f); break;
+			case 3: d = make_float4(alpha, alpha, alpha, 0.f); break;
+			case 4: d = fetch_rgba16f(A.velocity, A.in_w, A.in_h, x, y, st); break;
+			case 5: d = make_float4(pixelSpeed, 0.f, 0.f, 0.f); break;
+			case 6: d = toScreen; break;
+			case 7: d = toHistory; break;
+			case 8:
+				switch (seg & 3u) {
+					case 0: d = make_float4(0.f, 0.f, 1.f, 0.f); break;
+					case 1: d = make_float4(1.f, 0.f, 0.f, 0.f); break;
+					case 2: d = make_float4(1.f, 1.f, 0.f, 0.f); break;
+					default: break;
+				}
+				break;
+			default: break;
+		}
+		const float sc = P.mDebugScale;
+		d = make_float4(d.x * (P.mDebugMask[0] * sc), d.y * (P.mDebugMask[1] * sc), d.z * (P.mDebugMask[2] * sc), d.w * (P.mDebugMask[3] * sc));
+		if (P.mDebugCenter) d = make_float4(d.x * 0.5f + 0.5f, d.y * 0.5f + 0.5f, d.z * 0.5f + 0.5f, d.w * 0.5f + 0.5f);
+		st_rgba16f(A.debug, x, y, d);
+	}
+	if (genSeg) st_r32ui(A.segmask, x, y, seg);
+	st_r32ui(A.mask, x, y, (rejected ? 1u : 0u) | (rectified ? 2u : 0u) | (((unsigned int)P.mColorClampingOrClipping & 3u) << 2));
+}
+
+cudaError_t launch_resolve_generic(const ResolveArgs& args, cudaStream_t stream) {
+	dim3 block(32, 8);
+	dim3 grid((args.out_w + block.x - 1) / block.x, (args.band_rows + block.y - 1) / block.y);
+	taa_resolve_generic_kernel<<<grid, block, 0, stream>>>(args);
+	return cudaGetLastError();
+}
+
+}  // namespace taa

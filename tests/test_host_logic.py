@@ -1,0 +1,112 @@
+"""CPU: the pure-host helpers of the library (jitter, CasSetup, matrices) against the oracle and the known answers."""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from taa_star_b200 import abi, host
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def known():
+    return json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+
+
+def test_cas_setup_known_answer(taalib, oracle):
+    k = known()["cas_setup"]
+    for case in k:
+        pc = host.cas_setup(case["sharpness"], case["w"], case["h"])
+        assert list(pc.const0) == case["const0"], case
+        assert list(pc.const1) == case["const1"], case
+        c0, c1 = oracle.cas_setup(case["sharpness"], case["w"], case["h"])
+        assert c0 == case["const0"] and c1 == case["const1"], case
+
+
+def test_halton_known_answer(taalib, oracle):
+    k = known()["halton_2_3_8_px"]
+    for i, (hx, hy) in enumerate(k):
+        assert taalib.taa_halton(i + 1, 2) - 0.5 == pytest.approx(hx, abs=1e-6)
+        assert taalib.taa_halton(i + 1, 3) - 0.5 == pytest.approx(hy, abs=1e-6)
+        assert taalib.taa_halton(i + 1, 2) == oracle.halton(i + 1, 2)
+        assert taalib.taa_halton(i + 1, 3) == oracle.halton(i + 1, 3)
+    for b in (2, 3, 5):
+        for i in range(1, 200):
+            assert taalib.taa_halton(i, b) == oracle.halton(i, b)
+
+
+@pytest.mark.parametrize("dist", [0, 1, 2, 3, 4, 5])
+def test_jitter_patterns_match_oracle(oracle, dist):
+    dbg = [(0.1, -0.2), (0.3, 0.4), (-0.45, 0.05)] if dist == 5 else None
+    for (w, h) in ((1920, 1080), (3840, 2160), (333, 77)):
+        for frame in list(range(0, 40)) + [12345]:
+            for kw in (dict(), dict(fixed_index=2), dict(slow_motion=3), dict(rotate_degrees=30.0, extra_scale=1.5)):
+                a, n = host.jitter_offset_for_frame(frame, w, h, sample_distribution=dist, debug_offsets=dbg, **kw)
+                b, m = oracle.jitter(frame, w, h, sample_distribution=dist, debug_offsets=dbg, **kw)
+                assert n == m == {0: 4, 1: 4, 2: 8, 3: 16, 4: 16, 5: 3}[dist]
+                assert a == b, (dist, w, h, frame, kw)
+
+
+def test_jitter_is_within_half_a_pixel_and_halton_ndc_scale():
+    for frame in range(16):
+        (x, y), n = host.jitter_offset_for_frame(frame, 1920, 1080, sample_distribution=2)
+        assert abs(x) <= 1.0 / 1920 and abs(y) <= 1.0 / 1080
+    (x, y), _ = host.jitter_offset_for_frame(1, 1920, 1080, sample_distribution=2)
+    assert x == pytest.approx(-0.25 * 2 / 1920, rel=1e-6) and y == pytest.approx((1 / 3 + 1 / 9 - 0.5 + 0.0) * 0 + (2 / 3 - 0.5) * 2 / 1080, rel=1e-5)
+
+
+def test_jittered_projection_is_translate_times_proj(taalib):
+    rng = np.random.default_rng(1)
+    P = rng.standard_normal((4, 4)).astype(np.float32)  # P[row, col]
+    flat = P.T.reshape(-1)  # column-major
+    out = (C.c_float * 16)()
+    taalib.taa_jittered_projection((C.c_float * 16)(*flat), 0.25, -0.5, out)
+    T = np.eye(4, dtype=np.float32)
+    T[0, 3], T[1, 3] = 0.25, -0.5
+    want = (T @ P).T.reshape(-1)  # glm::translate(...) * P  (taa.hpp:248)
+    assert np.allclose(np.array(out[:]), want, rtol=1e-6, atol=1e-6)
+
+
+def test_reprojection_matrices(taalib):
+    from taa_star_b200.synth import SyntheticScene
+    sc = SyntheticScene(64, 36, with_aux=False)
+    P, V1, V0 = sc.proj_matrix(), sc.view_matrix(5), sc.view_matrix(4)
+    inv, hist = (C.c_float * 16)(), (C.c_float * 16)()
+    m = lambda a: (C.c_float * 16)(*a)
+    assert taalib.taa_reprojection_matrices(m(P), m(V1), m(P), m(V0), inv, hist) == 0
+    Pm, V1m, V0m = (np.array(a, dtype=np.float64).reshape(4, 4).T for a in (P, V1, V0))
+    assert np.allclose(np.array(inv[:]).reshape(4, 4).T, np.linalg.inv(Pm @ V1m), rtol=1e-5, atol=1e-6)
+    assert np.allclose(np.array(hist[:]).reshape(4, 4).T, Pm @ V0m, rtol=1e-6, atol=1e-6)
+    # a point on the plane reprojects by the pan: history uv = uv - pan/res
+    uv = np.array([0.3, 0.6])
+    clip = np.array([uv[0] * 2 - 1, uv[1] * 2 - 1, sc.ndc_depth(sc.plane_depth), 1.0])
+    world = np.array(inv[:]).reshape(4, 4).T @ clip
+    h = np.array(hist[:]).reshape(4, 4).T @ world
+    huv = h[:2] / h[3] * 0.5 + 0.5
+    assert np.allclose(uv - huv, [sc.pan[0] / sc.W, sc.pan[1] / sc.H], atol=1e-6)
+    sing = [0.0] * 16
+    assert taalib.taa_reprojection_matrices(m(sing), m(V1), m(P), m(V0), inv, hist) == abi.TAA_E_INVALID_ARG
+
+
+def test_postprocess_defaults(taalib):
+    pp = host.postprocess_default(1920, 1080)  # taa.hpp:101-111 evaluated by :352-359
+    assert list(pp.zoomSrcLTWH) == [(1920 - 20) // 2, (1080 - 20) // 2, 20, 20]
+    assert list(pp.zoomDstLTWH) == [1920 - 200 - 10, 10, 200, 200]
+    assert pp.splitX == -1 and pp.zoom == 0 and pp.showZoomBox == 1 and list(pp.debugL_mask) == [1, 1, 1, 0]
+
+
+def test_invokee_settings_defaults(taalib):
+    t = host.Taa(3)
+    s = t.settings
+    assert s.mTaaEnabled == 1 and s.mPostProcessEnabled == 1 and s.mSharpener == 0 and s.mSharpenFactor == 0.5  # taa.hpp:1351-1352,1418-1419
+    assert s.jitter.mSampleDistribution == 1 and s.jitter.mFixedJitterIndex == -1 and s.jitter.mJitterSlowMotion == 1  # taa.hpp:1353,1404-1407
+    assert s.mResetHistoryOnChange == 1
+    assert t.mParameters[0].mAlpha == pytest.approx(0.05) and t.execution_order() == 100 and t.taa_enabled()
+    t.mParameters[1].mAlpha = 0.25
+    assert t.mParameters[1].mAlpha == 0.25
+    with pytest.raises(Exception):
+        host.Taa(1)  # static_assert(CF > 1), taa.hpp:1005
+    t.close()
