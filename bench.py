@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — resolved Mpixels/s of the TAA resolve on N B200s (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3]
+
+N = 1 : one 3840x2160 stream, BASELINE configs[1] ("4K TAA resolve: YCoCg variance clip, Catmull-Rom history, alpha 0.1").
+        A step = one taa_resolve_ex call on one synthetic frame; history ping-pongs, inputs rotate through 4 frame sets
+        (4 x 166 MB, larger than the 126 MB L2), so every step streams its inputs from HBM.
+N > 1 : one 7680x4320 frame sharded by row bands over N ranks (BASELINE configs[3]); every step each rank resolves its band and
+        exchanges a history halo with its neighbours over NCCL (taa_star_b200/sharded.py). Launched with torchrun.
+--impl reference : the CPU restatement of the reference shader (oracle/, all host threads) on the same config; rank 0 only.
+Prints ONE JSON line (see the contract in the task description).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_PX = {2: 44, 3: 48}  # colour 8 + depth 4 + velocity 8 + history 8 | history out 8 + result 8 (+ history depth 4)
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                    r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def region(self, on: bool):
+        (self._active.set if on else self._active.clear)()
+
+    def result(self):
+        self._stop.set()
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_oracle_throughput(cfg_id: int, width: int, height: int, budget_s: float = 12.0):
+    """Times the CPU restatement (oracle/) on a band of rows of the bench workload. Returns (Mpx/s, cores, sample text)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle_py
+    from taa_star_b200 import configs
+    from taa_star_b200.synth import SyntheticScene
+    p = configs.config2_resolve() if cfg_id == 2 else configs.config3_full_chain()
+    sc = SyntheticScene(width, height, with_aux=False)
+    f0, f1 = sc.frame(8), sc.frame(9)
+    ins = dict(color=f1.color.numpy(), depth=f1.depth.numpy(), velocity=f1.velocity.numpy())
+    hist = f0.color.numpy().copy()
+    u = configs.uniforms_for(p, f1.jitter_ndc)
+    cores = oracle_py.max_threads()
+    rows = min(height, 64)
+    t0 = time.perf_counter()
+    oracle_py.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=f0.depth.numpy(), want=("history_out", "result"), rows=(height // 2, height // 2 + rows))
+    per_row = (time.perf_counter() - t0) / rows
+    rows = int(max(64, min(height, budget_s / 3 / max(per_row, 1e-9))))
+    y0 = (height - rows) // 2
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        oracle_py.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=f0.depth.numpy(), want=("history_out", "result"), rows=(y0, y0 + rows))
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return rows * width / best / 1e6, cores, f"{rows} rows of one {width}x{height} frame (config {cfg_id}), best of 3, {cores} OpenMP threads, oracle/libtaa_oracle.so"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg_id = args.config
+    width, height = (3840, 2160) if args.gpus == 1 else (7680, 4320)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    from taa_star_b200 import configs
+    from taa_star_b200.synth import SyntheticScene
+    p = configs.config2_resolve() if cfg_id == 2 else configs.config3_full_chain()
+    sc = SyntheticScene(3840, 2160, with_aux=False)  # the band sample is taken from a 4K frame in both cases (same per-pixel work)
+    f0, f1 = sc.frame(8), sc.frame(9)
+    hist = f0.color.numpy().copy()
+    u = configs.uniforms_for(p, f1.jitter_ndc)
+    cores = oracle_py.max_threads()
+    rows = 192  # bounded sample per step
+    y0 = (2160 - rows) // 2
+
+    def step():
+        oracle_py.resolve(u, f1.color.numpy(), f1.depth.numpy(), f1.velocity.numpy(), hist, history_depth=f0.depth.numpy(),
+                          want=("history_out", "result"), rows=(y0, y0 + rows))
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    mpx = args.steps * rows * 3840 / dt / 1e6
+    sample = f"each step = {rows} rows of a 3840x2160 frame (config {cfg_id}) through oracle/libtaa_oracle.so with {cores} OpenMP threads"
+    line = {"impl": "reference", "metric": "resolved Mpixels/s", "value": round(mpx, 3), "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{width}x{height} TAA resolve, BASELINE configs[{1 if cfg_id == 2 else 2}]", "sample": sample},
+            "cpu_baseline": {"value": round(mpx, 3), "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(mpx, 3), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_single(args):
+    import torch
+    from taa_star_b200 import abi, configs, host
+    from taa_star_b200.synth import SyntheticScene
+    W, H = args.width, args.height
+    cfg_id = args.config
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda:0")
+    p = configs.config2_resolve() if cfg_id == 2 else configs.config3_full_chain()
+    flags = abi.TAA_FLAG_FAST_FILTER if args.fast else 0
+    NSETS = 4
+    sc = SyntheticScene(W, H, device=dev, with_aux=False)
+    frames = [sc.frame(n) for n in range(NSETS)]
+    ctx = host.TaaContext((W, H), flags=flags)
+    hist = [torch.zeros(H, W, 4, dtype=torch.float16, device=dev) for _ in range(2)]
+    result = torch.zeros(H, W, 4, dtype=torch.float16, device=dev)
+    stream = torch.cuda.Stream()
+    sptr = stream.cuda_stream
+    # pre-built argument blocks: one per (frame set, history parity)
+    prepared = []
+    for n in range(NSETS):
+        f, fprev = frames[n], frames[(n - 1) % NSETS]
+        for par in range(2):
+            im = ctx.images(color=f.color, depth=f.depth, velocity=f.velocity, history_in=hist[par], history_out=hist[1 - par], result=result,
+                            history_depth=fprev.depth if cfg_id == 3 else None)
+            prepared.append((im, configs.uniforms_for(p, f.jitter_ndc)))
+    u0 = configs.uniforms_for(p, frames[0].jitter_ndc, reset_history=True)
+
+    def step(i):
+        im, u = prepared[(i % NSETS) * 2 + (i % 2)]
+        ctx.resolve_prepared(im, u, sptr)
+
+    with torch.cuda.stream(stream):
+        ctx.resolve_prepared(prepared[0][0], u0, sptr)
+        for i in range(1, args.warmup + 1):
+            step(i)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.region(True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(i + args.warmup + 1)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks.region(False)
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    px = W * H
+    mpx_s = args.steps * px / (ms * 1e-3) / 1e6
+    ms_per_step = ms / args.steps
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_PX[cfg_id] * px / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the invokee (taa<CF>::render path), H2D + D2H inside the timed region ----
+    t = host.Taa(3, flags=flags)
+    t.set_sizes_for_host_frames((W, H), (W, H))
+    for k, v in (("mUseYCoCg", p.mUseYCoCg),):
+        pass
+    for i in range(2):
+        C.memmove(C.addressof(t.mParameters[i]), C.addressof(p), C.sizeof(p))
+    s = t.settings
+    s.jitter.mSampleDistribution = 2
+    s.mPostProcessEnabled = 1 if cfg_id == 3 else 0
+    s.mSharpener = 2 if cfg_id == 3 else 0
+    s.mResetHistoryOnChange = 0
+    lib = abi.load_library()
+
+    def pinned(tensor):
+        n = tensor.numel() * tensor.element_size()
+        ptr = lib.taa_host_alloc(n)
+        assert ptr, "taa_host_alloc failed"
+        ht = torch.frombuffer((C.c_ubyte * n).from_address(ptr), dtype=torch.uint8).view(tensor.dtype).view(tensor.shape)
+        ht.copy_(tensor.cpu())
+        return ht
+    hsets = [(pinned(f.color), pinned(f.depth), pinned(f.velocity)) for f in frames]
+    houts = [pinned(result) for _ in range(3)]
+    e2e_steps = max(8, min(args.steps, 48))
+    for n in range(6):  # warm-up of the pipeline
+        f = frames[n % NSETS]
+        c, d, v = hsets[n % NSETS]
+        t.frame_host(n, c, d, v, f.view, f.proj, houts[n % 3])
+    for n in range(3, 6):
+        t.wait(n)
+    torch.cuda.synchronize()
+    clocks.region(True)
+    e2e_launch0 = t.launch_count
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        n = 6 + k
+        f = frames[n % NSETS]
+        c, d, v = hsets[n % NSETS]
+        t.frame_host(n, c, d, v, f.view, f.proj, houts[n % 3])
+    for n in range(6 + e2e_steps - 3, 6 + e2e_steps):
+        t.wait(n)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    clocks.region(False)
+    e2e_mpx = e2e_steps * px / e2e_dt / 1e6
+    h2d = px * (8 + 4 + 8)
+    d2h = px * 8
+    checksum = float(houts[(6 + e2e_steps - 1) % 3][::97, ::89, :3].float().mean())
+    assert 0.05 < checksum < 0.95, f"implausible result mean {checksum}"
+
+    cpu_mpx, cores, sample = cpu_oracle_throughput(cfg_id, W, H)
+    line = {
+        "metric": "resolved Mpixels/s", "value": round(mpx_s, 1), "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "fps": round(1e3 / ms_per_step, 1),
+        "config": {"workload": f"{W}x{H} TAA resolve, BASELINE configs[{1 if cfg_id == 2 else 2}] (config {cfg_id})", "arithmetic": "fast-filter" if args.fast else "exact",
+                   "l2": f"inputs larger than L2: {NSETS} frame sets rotated ({NSETS} x {px * 20 / 1e6:.0f} MB), history ping-pong",
+                   "outputs": "history_out + result"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                     "peak_source": peak_src, "bytes_per_px": BYTES_PER_PX[cfg_id], "kernel": "taa_resolve"},
+        "cpu_baseline": {"value": round(cpu_mpx, 3), "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(e2e_mpx, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "fps": round(e2e_steps / e2e_dt, 1), "path": "taa_invokee_frame_host: pinned host G-buffer -> H2D -> render() -> D2H of the final image, 3 frames in flight",
+                "gpu_launches": int(t.launch_count - e2e_launch0)},
+        "clocks": clocks.result(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3])
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--fast", action="store_true", help="TAA_FLAG_FAST_FILTER kernels")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20  # bounded: each step is ~1 s of CPU work
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 or world > 1:
+        from taa_star_b200 import sharded
+        return sharded.bench_main(args)
+    return run_single(args)
+
+
+if __name__ == "__main__":
+    main()
