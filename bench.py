@@ -295,7 +295,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 or world > 1:
         from taa_star_b200 import sharded
-        return sharded.bench_main(args)
+        return sharded.bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX)
     return run_single(args)
 
 

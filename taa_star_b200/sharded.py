@@ -1,0 +1,282 @@
+"""Row-band sharding of one large frame across GPUs (BASELINE configs[3]).
+
+The reference is single-GPU (source/main.cpp:4973); this is new work. Every output pixel of taa.comp depends on
+  (i)  current-frame inputs within a 1-texel apron (3x3 neighbourhood, taa.comp:199-213; 5-tap velocity test, :802-806), and
+  (ii) history_in within (motion + filter footprint) of the pixel (taa.comp:421, 441-513),
+so rank r of R resolves output rows [r*H/R, (r+1)*H/R) from band-local buffers that carry `halo` extra history rows above and
+below. With depth culling the previous frame's depth is read at the history position too (taa.comp:818), so that buffer needs
+the same halo: each rank keeps (or renders) depth for its band +- halo rows. After each frame a rank sends the first / last `halo` rows of the band it just wrote to its upper / lower neighbour
+(one grouped NCCL send/recv over NVLink). The boundary strips are resolved first so that the exchange overlaps the interior.
+If motion is unbounded, `replicate=True` all-gathers the whole history instead (correct for any motion, but a scaling cliff).
+
+One process per GPU; torch.distributed is the plumbing (NCCL on GPUs, gloo in the CPU tests of the exchange logic).
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def band_of(height: int, world: int, rank: int):
+    """Rows [y0, y1) owned by `rank`."""
+    return rank * height // world, (rank + 1) * height // world
+
+
+@dataclass
+class BandLayout:
+    height: int
+    world: int
+    rank: int
+    halo: int        # history rows kept above/below the band
+    apron: int = 2   # input rows kept above/below the band (3x3 neighbourhood + velocity taps + sampler bleed)
+
+    def __post_init__(self):
+        self.y0, self.y1 = band_of(self.height, self.world, self.rank)
+        self.hy0, self.hy1 = max(0, self.y0 - self.halo), min(self.height, self.y1 + self.halo)
+        self.iy0, self.iy1 = max(0, self.y0 - self.apron), min(self.height, self.y1 + self.apron)
+        smallest = min(b - a for a, b in (band_of(self.height, self.world, r) for r in range(self.world)))
+        if self.world > 1 and smallest < self.halo:
+            raise ValueError(f"halo {self.halo} exceeds the smallest band ({smallest} rows): use fewer ranks or replicate=True")
+
+    @property
+    def rows(self):
+        return self.y1 - self.y0
+
+
+class HaloExchanger:
+    """Moves the freshly written boundary rows of a band-local history buffer into the neighbours' halo rows."""
+
+    def __init__(self, layout: BandLayout, group=None):
+        self.L = layout
+        self.group = group
+
+    def ops(self, hist: torch.Tensor):
+        """hist: (hy1 - hy0, W, 4) band-local history buffer whose row 0 is global row hy0."""
+        L = self.L
+        ops = []
+        h = L.halo
+        if L.rank > 0:  # upper neighbour: it needs my first h rows; I need its last h rows
+            send = hist[L.y0 - L.hy0: L.y0 - L.hy0 + h]
+            recv = hist[L.y0 - h - L.hy0: L.y0 - L.hy0]
+            ops += [dist.P2POp(dist.isend, send, L.rank - 1, self.group), dist.P2POp(dist.irecv, recv, L.rank - 1, self.group)]
+        if L.rank < L.world - 1:
+            send = hist[L.y1 - h - L.hy0: L.y1 - L.hy0]
+            recv = hist[L.y1 - L.hy0: L.y1 - L.hy0 + h]
+            ops += [dist.P2POp(dist.isend, send, L.rank + 1, self.group), dist.P2POp(dist.irecv, recv, L.rank + 1, self.group)]
+        return ops
+
+    def exchange(self, hist: torch.Tensor):
+        ops = self.ops(hist)
+        if not ops:
+            return []
+        return dist.batch_isend_irecv(ops)
+
+
+def gather_full_history(band: torch.Tensor, full: torch.Tensor, layout: BandLayout, group=None):
+    """replicate=True: all-gather the bands of history_out into a full-frame buffer on every rank."""
+    sizes = [band_of(layout.height, layout.world, r) for r in range(layout.world)]
+    if len({b - a for a, b in sizes}) == 1:
+        dist.all_gather_into_tensor(full, band.contiguous(), group=group)
+    else:
+        outs = [full[a:b] for a, b in sizes]
+        dist.all_gather(outs, band.contiguous(), group=group)
+
+
+class ShardedTaa:
+    """One rank's share of a row-band sharded resolve. Inputs for the band (plus apron) are produced locally."""
+
+    def __init__(self, width: int, height: int, halo: int = 20, replicate: bool = False, flags: int = 0, device=None, group=None, apron: int = 2):
+        from . import host
+        self.W, self.H = width, height
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.L = BandLayout(height, self.world, self.rank, halo, apron)
+        self.replicate = replicate
+        self.group = group
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        L = self.L
+        rows = (height if replicate else L.hy1 - L.hy0)
+        self.hist_y0 = 0 if replicate else L.hy0
+        self.hist = [torch.zeros(rows, width, 4, dtype=torch.float16, device=self.device) for _ in range(2)]
+        self.result = torch.zeros(L.rows, width, 4, dtype=torch.float16, device=self.device)
+        self.band_tmp = torch.zeros(L.rows, width, 4, dtype=torch.float16, device=self.device) if replicate else None
+        # three sub-bands: the two boundary strips (exchanged) first, then the interior
+        h = min(halo, L.rows // 2) if (self.world > 1 and not replicate) else 0
+        strips = []
+        if h and L.rank > 0:
+            strips.append((L.y0, h))
+        if h and L.rank < L.world - 1:
+            strips.append((L.y1 - h, h))
+        a = L.y0 + (h if (h and L.rank > 0) else 0)
+        b = L.y1 - (h if (h and L.rank < L.world - 1) else 0)
+        self.boundary = [host.TaaContext((width, height), band=s, flags=flags) for s in strips]
+        self.interior = host.TaaContext((width, height), band=(a, b - a), flags=flags) if b > a else None
+        self.xchg = HaloExchanger(L, group)
+        self.compute = torch.cuda.Stream(device=self.device)
+        self.comm = torch.cuda.Stream(device=self.device)
+        self.ev_boundary = torch.cuda.Event()
+        self.ev_comm = torch.cuda.Event()
+        self.parity = 0
+        self._pending = []
+
+    @property
+    def launch_count(self):
+        return sum(c.launch_count for c in self.boundary) + (self.interior.launch_count if self.interior else 0)
+
+    def step(self, uniforms, color, depth, velocity, in_y0: int, history_depth=None):
+        """Resolves this rank's band for one frame. color/depth/velocity hold input rows starting at global row in_y0."""
+        L = self.L
+        hin, hout = self.hist[self.parity], self.hist[1 - self.parity]
+        kw = dict(color=(color, in_y0), depth=(depth, in_y0), velocity=(velocity, in_y0), history_in=(hin, self.hist_y0),
+                  history_out=(hout, self.hist_y0), result=(self.result, L.y0))
+        if history_depth is not None:
+            kw["history_depth"] = (history_depth, in_y0)
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(self.ev_comm)  # halos of `hin` (written by the previous exchange) must have landed
+            for c in self.boundary:
+                c.resolve(uniforms, stream=self.compute, **kw)
+            self.ev_boundary.record(self.compute)
+            if self.interior is not None:
+                self.interior.resolve(uniforms, stream=self.compute, **kw)
+        if self.world > 1:
+            if self.replicate:
+                with torch.cuda.stream(self.compute):
+                    band = hout[L.y0:L.y1]
+                    gather_full_history(band, hout, L, self.group)
+                    self.ev_comm.record(self.compute)
+            else:
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(self.ev_boundary)
+                    for w in self._pending:
+                        w.wait()
+                    self._pending = self.xchg.exchange(hout)
+                    for w in self._pending:
+                        w.wait()
+                    self._pending = []
+                    self.ev_comm.record(self.comm)
+        self.parity ^= 1
+
+    def poll(self) -> int:
+        st = 0
+        for c in self.boundary + ([self.interior] if self.interior else []):
+            st = min(st, c.poll_status(self.compute))
+        return st
+
+
+# ---- bench (N > 1) ------------------------------------------------------------------------------------------------------------------
+def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
+    from . import abi, configs
+    from .synth import SyntheticScene
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    W, H = (7680, 4320) if (args.width, args.height) == (3840, 2160) else (args.width, args.height)
+    cfg_id = args.config
+    p = configs.config2_resolve() if cfg_id == 2 else configs.config3_full_chain()
+    flags = abi.TAA_FLAG_FAST_FILTER if args.fast else 0
+    halo = 20  # |v_y| <= 16 px guaranteed by the generator + 2 filter + 2 guard
+    sh = ShardedTaa(W, H, halo=halo, flags=flags, device=dev, apron=halo if cfg_id == 3 else 2)
+    L = sh.L
+    NSETS = 4
+    sc = SyntheticScene(W, H, device=dev, with_aux=False, rows=(L.iy0, L.iy1))
+    frames = [sc.frame(n) for n in range(NSETS)]
+    unis = [configs.uniforms_for(p, f.jitter_ndc) for f in frames]
+    u0 = configs.uniforms_for(p, frames[0].jitter_ndc, reset_history=True)
+
+    def step(i, u=None):
+        f, fp = frames[i % NSETS], frames[(i - 1) % NSETS]
+        sh.step(u or unis[i % NSETS], f.color, f.depth, f.velocity, L.iy0, history_depth=fp.depth if cfg_id == 3 else None)
+
+    step(0, u0)
+    for i in range(1, args.warmup + 1):
+        step(i)
+    torch.cuda.synchronize()
+    assert sh.poll() == abi.TAA_OK, "halo overflow during warm-up"
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = sh.launch_count
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if clocks:
+        clocks.region(True)
+    ev0.record(sh.compute)
+    for i in range(args.steps):
+        step(i + args.warmup + 1)
+    sh.compute.wait_event(sh.ev_comm)
+    ev1.record(sh.compute)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if clocks:
+        clocks.region(False)
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = torch.tensor([sh.launch_count - launches0], device=dev)
+    dist.all_reduce(launches)
+    # kernel-only time of this rank's interior + boundary launches is not separable from the exchange here; the roofline entry uses
+    # the per-step time of the whole sharded step (conservative).
+    px = W * H
+    ms_per_step = ms / args.steps
+    mpx_s = px / (ms_per_step * 1e-3) / 1e6
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_PX[cfg_id] * px / world / (ms_per_step * 1e-3) / 1e9  # per GPU
+
+    # ---- e2e: band inputs from pinned host memory, result band back to the host, every step ----
+    hcol = [f.color.cpu().pin_memory() for f in frames]
+    hdep = [f.depth.cpu().pin_memory() for f in frames]
+    hvel = [f.velocity.cpu().pin_memory() for f in frames]
+    hres = torch.empty_like(sh.result, device="cpu").pin_memory()
+    dcol, ddep, dvel = torch.empty_like(frames[0].color), torch.empty_like(frames[0].depth), torch.empty_like(frames[0].velocity)
+    e2e_steps = max(8, min(args.steps, 32))
+
+    def e2e_step(i):
+        k = i % NSETS
+        with torch.cuda.stream(sh.compute):
+            dcol.copy_(hcol[k], non_blocking=True)
+            ddep.copy_(hdep[k], non_blocking=True)
+            dvel.copy_(hvel[k], non_blocking=True)
+        sh.step(unis[k], dcol, ddep, dvel, L.iy0, history_depth=None if cfg_id == 2 else frames[(i - 1) % NSETS].depth)
+        with torch.cuda.stream(sh.compute):
+            hres.copy_(sh.result, non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i + 3)
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_mpx = e2e_steps * px / float(dt.item()) / 1e6
+    in_rows = L.iy1 - L.iy0
+    if rank == 0:
+        line = {
+            "metric": "resolved Mpixels/s", "value": round(mpx_s, 1), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "fps": round(1e3 / ms_per_step, 1),
+            "config": {"workload": f"{W}x{H} TAA resolve sharded in {world} row bands, BASELINE configs[3] (config {cfg_id} settings)",
+                       "arithmetic": "fast-filter" if args.fast else "exact", "halo_rows": halo,
+                       "exchange": "NCCL send/recv of 2 x halo rows of history per neighbour per frame, overlapped with the interior resolve",
+                       "l2": f"inputs larger than L2: {NSETS} frame sets rotated, history ping-pong"},
+            "gpu_launches": int(launches.item()),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                         "peak_source": peak_src, "bytes_per_px": BYTES_PER_PX[cfg_id], "kernel": "taa_resolve (per GPU, whole sharded step incl. exchange)"},
+            "cpu_baseline": None,
+            "e2e": {"value": round(e2e_mpx, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": in_rows * W * 20 * world, "d2h_bytes_per_step": px * 8, "steps": e2e_steps,
+                    "path": "per rank: pinned host band (+apron) -> H2D -> band resolve + halo exchange -> D2H of the result band"},
+            "clocks": clocks.result() if clocks else None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

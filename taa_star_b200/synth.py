@@ -59,7 +59,7 @@ class Frame:
 class SyntheticScene:
     def __init__(self, width: int, height: int, pan_px=(3.0, 0.5), mover_px=(-6.0, 0.0), seed: int = 0x7AA57A2,
                  device="cpu", fov_deg: float = 60.0, near: float = 0.1, far: float = 100.0, jitter_len: int = 8,
-                 plane_depth: float = 10.0, mover_depth: float = 4.0, with_aux: bool = True):
+                 plane_depth: float = 10.0, mover_depth: float = 4.0, with_aux: bool = True, rows=None):
         self.W, self.H = int(width), int(height)
         self.pan = (float(pan_px[0]), float(pan_px[1]))
         self.mover = (float(mover_px[0]), float(mover_px[1]))
@@ -80,7 +80,9 @@ class SyntheticScene:
         self.phase = (torch.rand(6, 3, generator=g) * 2 * math.pi).to(self.device)
         self.m0 = (0.62 * self.W, 0.45 * self.H)          # mover centre at frame 0 (px)
         self.mhalf = (0.11 * self.W, 0.16 * self.H)        # mover half extent (px)
-        ys, xs = torch.meshgrid(torch.arange(self.H, dtype=torch.float32, device=self.device),
+        # rows = (a, b): generate only image rows [a, b) of the W x H frame (one band of a sharded frame)
+        self.row0, self.row1 = rows if rows is not None else (0, self.H)
+        ys, xs = torch.meshgrid(torch.arange(self.row0, self.row1, dtype=torch.float32, device=self.device),
                                 torch.arange(self.W, dtype=torch.float32, device=self.device), indexing="ij")
         self.xs, self.ys = xs + 0.5, ys + 0.5
 
@@ -148,7 +150,7 @@ class SyntheticScene:
         color = torch.cat([rgb, torch.ones_like(rgb[..., :1])], dim=-1).to(torch.float16)
         zb, zm = self.ndc_depth(self.plane_depth), self.ndc_depth(self.mover_depth)
         depth = torch.where(inside, torch.full_like(sx, zm), torch.full_like(sx, zb)).to(torch.float32)
-        vel = torch.zeros(H, W, 4, dtype=torch.float32, device=self.device)
+        vel = torch.zeros(self.row1 - self.row0, W, 4, dtype=torch.float32, device=self.device)
         vel[..., 0] = torch.where(inside, torch.full_like(sx, self.mover[0] / W), torch.full_like(sx, self.pan[0] / W))
         vel[..., 1] = torch.where(inside, torch.full_like(sx, self.mover[1] / H), torch.full_like(sx, self.pan[1] / H))
         vel[..., 3] = inside.to(torch.float32)

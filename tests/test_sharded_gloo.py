@@ -1,0 +1,108 @@
+"""CPU, world_size 2 and 3 over gloo: the band layout, the halo exchange and the replicated-history gather of
+taa_star_b200/sharded.py. The per-band compute is done by the oracle here (no GPU), which also proves the halo sizing rule:
+a band with `halo` rows of history (and of the previous depth buffer, which taa.comp:818 reads at the HISTORY position) and a
+2-row apron of the current inputs reproduces the whole-frame result exactly."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, replicate, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle_py
+        from taa_star_b200 import configs
+        from taa_star_b200.sharded import BandLayout, HaloExchanger, band_of, gather_full_history
+        from taa_star_b200.synth import SyntheticScene
+        W, H, halo = 96, 66, 9
+        L = BandLayout(H, world, rank, halo)
+        assert (L.y0, L.y1) == band_of(H, world, rank)
+        sc = SyntheticScene(W, H, pan_px=(2.0, 5.5), mover_px=(-4.0, 3.0), with_aux=False)
+        p = configs.config3_full_chain()
+        xchg = HaloExchanger(L)
+        # every rank also runs the whole frame (the reference result)
+        full_hist = np.zeros((H, W, 4), np.float16)
+        # band-local state: full-size arrays poisoned outside the rows this rank may touch
+        band_hist = torch.full((H, W, 4), float("nan"), dtype=torch.float16)
+        band_hist[L.hy0:L.hy1] = 0
+        prev_depth = None
+        for n in range(6):
+            f = sc.frame(n)
+            u = configs.uniforms_for(p, f.jitter_ndc, reset_history=(n == 0))
+            col, dep, vel = f.color.numpy(), f.depth.numpy(), f.velocity.numpy()
+            hd = prev_depth if prev_depth is not None else dep
+            ref = oracle_py.resolve(u, col, dep, vel, full_hist, history_depth=hd, want=("history_out", "result", "mask"))
+            # band: inputs poisoned outside the apron rows
+            def poison(a, lo, hi):
+                b = a.copy()
+                b[:lo] = np.nan if a.dtype != np.uint32 else 0
+                b[hi:] = np.nan if a.dtype != np.uint32 else 0
+                return b
+            got = oracle_py.resolve(u, poison(col, L.iy0, L.iy1), poison(dep, L.iy0, L.iy1), poison(vel, L.iy0, L.iy1), band_hist.numpy(),
+                                    history_depth=poison(hd, L.hy0, L.hy1), want=("history_out", "result", "mask"), rows=(L.y0, L.y1))
+            for k in ("history_out", "result"):
+                a, b = ref[k][L.y0:L.y1].view(np.uint16), got[k][L.y0:L.y1].view(np.uint16)
+                assert (a == b).all(), f"rank {rank} frame {n}: {k} differs from the whole-frame result"
+            assert (ref["mask"][L.y0:L.y1] == got["mask"][L.y0:L.y1]).all()
+            new_hist = torch.full((H, W, 4), float("nan"), dtype=torch.float16)
+            new_hist[L.y0:L.y1] = torch.from_numpy(got["history_out"][L.y0:L.y1])
+            if replicate:
+                full = torch.zeros((H, W, 4), dtype=torch.float16)
+                gather_full_history(new_hist[L.y0:L.y1], full, L)
+                assert (full.numpy().view(np.uint16) == ref["history_out"].view(np.uint16)).all()
+                new_hist = full
+            else:
+                view = new_hist[L.hy0:L.hy1]
+                for w in xchg.exchange(view):
+                    w.wait()
+                a = new_hist[L.hy0:L.hy1].numpy().view(np.uint16)
+                b = ref["history_out"][L.hy0:L.hy1].view(np.uint16)
+                assert (a == b).all(), f"rank {rank} frame {n}: halo rows differ after the exchange"
+            band_hist = new_hist
+            full_hist = ref["history_out"]
+            prev_depth = dep
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,replicate", [(2, False), (3, False), (2, True)])
+def test_band_sharding_over_gloo(world, replicate):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + world * 7 + (3 if replicate else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, replicate, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(msg == "ok" for _, msg in results), results
+
+
+def test_band_layout_rules():
+    sys.path.insert(0, ROOT)
+    from taa_star_b200.sharded import BandLayout, band_of
+    for H, R in ((4320, 8), (2160, 7), (66, 3)):
+        rows = [band_of(H, R, r) for r in range(R)]
+        assert rows[0][0] == 0 and rows[-1][1] == H and all(rows[i][1] == rows[i + 1][0] for i in range(R - 1))
+    L = BandLayout(4320, 8, 3, 20)
+    assert (L.y0, L.y1, L.hy0, L.hy1, L.iy0, L.iy1) == (1620, 2160, 1600, 2180, 1618, 2162)
+    assert BandLayout(4320, 8, 0, 20).hy0 == 0 and BandLayout(4320, 8, 7, 20).hy1 == 4320
+    with pytest.raises(ValueError):
+        BandLayout(64, 8, 0, 20)
