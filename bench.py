@@ -159,7 +159,7 @@ def run_single(args):
     torch.cuda.set_device(0)
     dev = torch.device("cuda:0")
     p = configs.config2_resolve() if cfg_id == 2 else configs.config3_full_chain()
-    flags = abi.TAA_FLAG_FAST_FILTER if args.fast else 0
+    flags = abi.TAA_FLAG_EXACT if args.exact else 0
     NSETS = 4
     sc = SyntheticScene(W, H, device=dev, with_aux=False)
     frames = [sc.frame(n) for n in range(NSETS)]
@@ -261,7 +261,7 @@ def run_single(args):
         "metric": "resolved Mpixels/s", "value": round(mpx_s, 1), "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "fps": round(1e3 / ms_per_step, 1),
-        "config": {"workload": f"{W}x{H} TAA resolve, BASELINE configs[{1 if cfg_id == 2 else 2}] (config {cfg_id})", "arithmetic": "fast-filter" if args.fast else "exact",
+        "config": {"workload": f"{W}x{H} TAA resolve, BASELINE configs[{1 if cfg_id == 2 else 2}] (config {cfg_id})", "arithmetic": "exact general kernel" if args.exact else "tuned kernel + exact fix-up pass",
                    "l2": f"inputs larger than L2: {NSETS} frame sets rotated ({NSETS} x {px * 20 / 1e6:.0f} MB), history ping-pong",
                    "outputs": "history_out + result"},
         "gpu_launches": int(launches),
@@ -285,7 +285,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3])
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
-    ap.add_argument("--fast", action="store_true", help="TAA_FLAG_FAST_FILTER kernels")
+    ap.add_argument("--exact", action="store_true", help="TAA_FLAG_EXACT: force the exact general kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -213,12 +213,16 @@ typedef struct taa_post_chain {
 /* ---- context ---- */
 enum {
 	TAA_FLAG_DEFAULT     = 0,
-	/* Arithmetic mode of the resolve kernels.
-	 * EXACT: every fp32 operation is performed in the order of the reference shader with IEEE
-	 *        round-to-nearest and no contraction; outputs are bit-identical to oracle/ on finite inputs.
-	 * FAST : colour filtering is re-associated and contracted (history footprint evaluated with direct
-	 *        separable weights); coordinates, depth/velocity predicates stay exact. Colour within 2^-10. */
-	TAA_FLAG_FAST_FILTER = 1u << 0
+	/* Arithmetic of the resolve kernels.
+	 * default: settings blocks of the tuned family (YCoCg variance clip, clipAabb, Catmull-Rom history, velocity
+	 *        reprojection; BASELINE configs 2-5) run on the shared-memory tiled kernel: coordinates and every
+	 *        rejection predicate are evaluated exactly, colour filtering is re-associated and contracted (within
+	 *        ~1e-5 of the exact result, gate 2^-10), and the pixels whose `rectified` predicate sits near its
+	 *        threshold are recomputed exactly by a second small launch, so integer masks are bit-exact.
+	 *        Every other settings block runs on the exact general kernel.
+	 * EXACT: always the general kernel: every fp32 operation in the order of the reference shader with IEEE
+	 *        round-to-nearest and no contraction; all outputs bit-identical to oracle/ on finite inputs. */
+	TAA_FLAG_EXACT = 1u << 0
 };
 
 typedef struct taa_desc {
@@ -271,6 +275,10 @@ TAA_API int taa_post_process(taa_ctx* ctx, const taa_image* src, const taa_image
 
 /* number of CUDA kernels launched through this context so far (bench.py reports it as gpu_launches) */
 TAA_API long long taa_launch_count(const taa_ctx* ctx);
+
+/* pixels the last resolve of this context handed from the tuned kernel to its exact fix-up pass (0 when the general
+ * kernel ran); synchronises `stream`. Diagnostic only. */
+TAA_API long long taa_fixup_pixels(taa_ctx* ctx, void* stream);
 
 /* reads and clears the device-side status word of the last resolves (halo overflow); synchronises `stream` */
 TAA_API int taa_poll_status(taa_ctx* ctx, void* stream);

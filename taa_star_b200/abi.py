@@ -12,7 +12,7 @@ import os
 ABI_VERSION = 1
 
 TAA_OK, TAA_E_INVALID_ARG, TAA_E_UNSUPPORTED, TAA_E_CUDA, TAA_E_NCCL, TAA_E_HALO_OVERFLOW = 0, -1, -2, -3, -4, -5
-TAA_FLAG_DEFAULT, TAA_FLAG_FAST_FILTER = 0, 1
+TAA_FLAG_DEFAULT, TAA_FLAG_EXACT = 0, 1
 
 # shaders/shader_cpu_common.h:31-40
 TAA_RTFLAG_OUT, TAA_RTFLAG_DIS, TAA_RTFLAG_NRM, TAA_RTFLAG_DPT = 0x1, 0x2, 0x4, 0x8
@@ -124,6 +124,7 @@ SIGNATURES = {
     "taa_post_process": (C.c_int, [_vp, _P(taa_image), _P(taa_image), _P(taa_image), _P(TaaPostProcessPush), _vp]),
     "taa_launch_count": (_ll, [_vp]),
     "taa_poll_status": (C.c_int, [_vp, _vp]),
+    "taa_fixup_pixels": (_ll, [_vp, _vp]),
     "taa_cas_setup": (None, [_P(TaaCasPush), _f32, _f32, _f32]),
     "taa_parameters_default": (None, [_P(TaaParameters)]),
     "taa_uniforms_default": (None, [_P(TaaUniforms)]),

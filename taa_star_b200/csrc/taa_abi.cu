@@ -106,9 +106,10 @@ int build_resolve_args(taa_ctx* c, const taa_resolve_images* im, const TaaUnifor
 }
 
 int run_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s) {
-	cudaError_t e = dispatch_resolve(c, A, s);
+	int launched = 0;
+	cudaError_t e = dispatch_resolve(c, A, s, &launched);
+	c->launches += launched;
 	if (e != cudaSuccess) return cuda_fail(c, e, "taa resolve launch");
-	c->launches++;
 	return TAA_OK;
 }
 
@@ -190,6 +191,8 @@ void taa_destroy(taa_ctx* c) {
 	cudaSetDevice(c->desc.device);
 	if (c->d_status) cudaFree(c->d_status);
 	for (void* p : c->scratch) if (p) cudaFree(p);
+	if (c->fix_list) cudaFree(c->fix_list);
+	if (c->fix_count) cudaFree(c->fix_count);
 	delete c;
 }
 
@@ -323,6 +326,16 @@ int taa_poll_status(taa_ctx* c, void* stream) {
 }
 
 long long taa_launch_count(const taa_ctx* c) { return c ? c->launches : 0; }
+
+long long taa_fixup_pixels(taa_ctx* c, void* stream) {
+	if (!c) return TAA_E_INVALID_ARG;
+	if (!c->fix_count || !c->last_was_tuned) return 0;
+	unsigned int h = 0;
+	cudaError_t e = cudaMemcpyAsync(&h, c->fix_count + (c->fix_parity ^ 1), sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+	if (e != cudaSuccess) return cuda_fail(c, e, "taa_fixup_pixels");
+	return (long long)h;
+}
 
 // ================================ pure host helpers ================================================
 

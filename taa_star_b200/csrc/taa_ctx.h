@@ -10,6 +10,10 @@ struct taa_ctx {
 	int num_sms = 0;
 	unsigned int* d_status = nullptr;  // device status word written by the kernels (halo overflow)
 	void* scratch[2] = {nullptr, nullptr};  // rgba16f out-res images for the unfused follow-on passes
+	unsigned int* fix_list = nullptr;  // pixels the tuned kernel hands to the exact fix-up pass (one slot per band pixel)
+	unsigned int* fix_count = nullptr; // two counters, used alternately: call n appends to [n & 1] and zeroes [(n + 1) & 1]
+	int fix_parity = 0;
+	bool last_was_tuned = false;
 	long long launches = 0;            // kernels launched through this context
 	std::string last_error;
 };
@@ -20,5 +24,5 @@ int cuda_fail(taa_ctx* c, cudaError_t e, const char* what);
 int build_resolve_args(taa_ctx* c, const taa_resolve_images* im, const TaaUniforms* u, ResolveArgs& A);
 int run_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s);
 // picks the kernel for this settings block: a tuned variant when one covers it, else the generic one
-cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s);
+cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, int* launched);
 }  // namespace taa

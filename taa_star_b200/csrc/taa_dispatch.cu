@@ -4,9 +4,36 @@
 
 namespace taa {
 
-cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s) {
-	(void)c;
-	return launch_resolve_generic(A, s);
+static cudaError_t ensure_fix_buffers(taa_ctx* c) {
+	if (c->fix_list) return cudaSuccess;
+	cudaError_t e = cudaMalloc(&c->fix_list, (size_t)c->desc.out_width * c->desc.band_rows * sizeof(unsigned int));
+	if (e != cudaSuccess) return e;
+	e = cudaMalloc(&c->fix_count, 2 * sizeof(unsigned int));
+	if (e != cudaSuccess) return e;
+	return cudaMemset(c->fix_count, 0, 2 * sizeof(unsigned int));
+}
+
+// Returns the number of kernels launched through *launched.
+cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, int* launched) {
+	*launched = 0;
+	if (!(c->desc.flags & TAA_FLAG_EXACT) && tuned_supports(A)) {
+		c->last_was_tuned = true;
+		cudaError_t e = ensure_fix_buffers(c);
+		if (e != cudaSuccess) return e;
+		unsigned int* cnt = c->fix_count + c->fix_parity;
+		unsigned int* cnt_next = c->fix_count + (c->fix_parity ^ 1);
+		c->fix_parity ^= 1;
+		e = launch_resolve_tuned(A, c->fix_list, cnt, cnt_next, s);
+		if (e != cudaSuccess) return e;
+		*launched = 1;
+		e = launch_resolve_fixup(A, c->fix_list, cnt, A.result.p != nullptr, c->num_sms, s);
+		if (e == cudaSuccess) *launched = 2;
+		return e;
+	}
+	c->last_was_tuned = false;
+	cudaError_t e = launch_resolve_generic(A, s);
+	if (e == cudaSuccess) *launched = 1;
+	return e;
 }
 
 }  // namespace taa

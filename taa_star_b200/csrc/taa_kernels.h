@@ -7,6 +7,15 @@ namespace taa {
 
 // taa.comp, fully general, exact arithmetic (taa_resolve_generic.cu)
 cudaError_t launch_resolve_generic(const ResolveArgs& args, cudaStream_t stream);
+// the same exact arithmetic on a device-side list of pixels (y * out_w + x), count read on the device
+cudaError_t launch_resolve_fixup(const ResolveArgs& args, const unsigned int* list, const unsigned int* count, bool write_screen, int num_sms,
+                                 cudaStream_t stream);
+
+// taa.comp for the BASELINE configs 2-5 family of settings, tiled through shared memory (taa_resolve_tuned.cu).
+// Appends the pixels whose `rectified` bit needs the exact arithmetic to fix_list / *fix_count and zeroes *fix_count_next.
+bool tuned_supports(const ResolveArgs& args);
+cudaError_t launch_resolve_tuned(const ResolveArgs& args, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next,
+                                 cudaStream_t stream);
 
 // follow-on passes, one kernel each as the reference dispatches them (taa_post.cu)
 struct PostImg { Img src; Img debug; ImgW dst; int w, h; };

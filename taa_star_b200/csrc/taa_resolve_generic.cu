@@ -182,11 +182,11 @@ struct Px {
 
 }  // namespace
 
-// main()                                                                              taa.comp:708-960
-__global__ void __launch_bounds__(256) taa_resolve_generic_kernel(const __grid_constant__ ResolveArgs A) {
-	const int x = blockIdx.x * blockDim.x + threadIdx.x;
-	const int y = A.band_y0 + blockIdx.y * blockDim.y + threadIdx.y;
-	if (x >= A.out_w || y >= A.band_y0 + A.band_rows || y >= A.out_h) return;
+// main() for one output pixel                                                         taa.comp:708-960
+// WRITE_SCREEN = false: the screen result is left alone (fix-up of a fused frame, where the follow-on passes
+// already consumed the tuned kernel's on-chip result).
+template <bool WRITE_SCREEN>
+__device__ __forceinline__ void resolve_pixel_exact(const ResolveArgs& A, const int x, const int y) {
 	unsigned int* st = A.status;
 
 	const TaaParameters& P = A.ubo.param[(A.ubo.splitScreen && x > A.ubo.splitX) ? 1 : 0];
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) taa_resolve_generic_kernel(const __grid_c
 	if (P.mPassThrough) {  // taa.comp:726-731
 		float4 c = fetch_rgba16f(A.color, A.in_w, A.in_h, lx, ly, st);
 		float4 h = fetch_rgba16f(A.history_in, A.out_w, A.out_h, x, y, st);
-		st_rgba16f(A.result, x, y, make_float4(c.x, c.y, c.z, 1.f));
+		if (WRITE_SCREEN) st_rgba16f(A.result, x, y, make_float4(c.x, c.y, c.z, 1.f));
 		st_rgba16f(A.history_out, x, y, make_float4(h.x, h.y, h.z, 1.f));
 		st_rgba16f(A.debug, x, y, make_float4(0.f, 0.f, 0.f, 0.f));
 		st_r32ui(A.mask, x, y, 0u);
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) taa_resolve_generic_kernel(const __grid_c
 	}
 	if (A.ubo.mBypassHistoryUpdate) {  // taa.comp:732-737
 		float4 h = fetch_rgba16f(A.history_in, A.out_w, A.out_h, x, y, st);
-		st_rgba16f(A.result, x, y, make_float4(h.x, h.y, h.z, 1.f));
+		if (WRITE_SCREEN) st_rgba16f(A.result, x, y, make_float4(h.x, h.y, h.z, 1.f));
 		st_rgba16f(A.history_out, x, y, make_float4(h.x, h.y, h.z, 1.f));
 		st_rgba16f(A.debug, x, y, make_float4(0.f, 0.f, 0.f, 0.f));
 		st_r32ui(A.mask, x, y, 0u);
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(256) taa_resolve_generic_kernel(const __grid_c
 	const float4 toScreen = mk4(P.mToneMapLumaKaris ? un_tonemap_karis(aa) : aa, 1.0f);
 
 	st_rgba16f(A.history_out, x, y, toHistory);
-	st_rgba16f(A.result, x, y, toScreen);
+	if (WRITE_SCREEN) st_rgba16f(A.result, x, y, toScreen);
 
 	if (A.debug.p) {  // taa.comp:912-942, 957
 		float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -461,10 +461,39 @@ __global__ void __launch_bounds__(256) taa_resolve_generic_kernel(const __grid_c
 	st_r32ui(A.mask, x, y, (rejected ? 1u : 0u) | (rectified ? 2u : 0u) | (((unsigned int)P.mColorClampingOrClipping & 3u) << 2));
 }
 
+__global__ void __launch_bounds__(256) taa_resolve_generic_kernel(const __grid_constant__ ResolveArgs A) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = A.band_y0 + blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= A.out_w || y >= A.band_y0 + A.band_rows || y >= A.out_h) return;
+	resolve_pixel_exact<true>(A, x, y);
+}
+
+// Fix-up pass of the tuned kernels (taa_resolve_tuned.cu): the pixels whose `rectified` predicate
+// (taa.comp:845) the re-associated arithmetic could not decide safely are recomputed here with the
+// exact arithmetic, from the inputs alone. `list` holds pixels packed as y * out_w + x.
+template <bool WRITE_SCREEN>
+__global__ void __launch_bounds__(128) taa_resolve_fixup_kernel(const __grid_constant__ ResolveArgs A, const unsigned int* __restrict__ list,
+                                                                const unsigned int* __restrict__ count) {
+	const unsigned int n = *count;
+	for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const unsigned int p = list[i];
+		const int y = (int)(p / (unsigned int)A.out_w), x = (int)(p - (unsigned int)y * (unsigned int)A.out_w);
+		resolve_pixel_exact<WRITE_SCREEN>(A, x, y);
+	}
+}
+
 cudaError_t launch_resolve_generic(const ResolveArgs& args, cudaStream_t stream) {
 	dim3 block(32, 8);
 	dim3 grid((args.out_w + block.x - 1) / block.x, (args.band_rows + block.y - 1) / block.y);
 	taa_resolve_generic_kernel<<<grid, block, 0, stream>>>(args);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_fixup(const ResolveArgs& args, const unsigned int* list, const unsigned int* count, bool write_screen, int num_sms,
+                                 cudaStream_t stream) {
+	const int grid = num_sms * 8;  // the count lives on the device: surplus CTAs find nothing to do and exit
+	if (write_screen) taa_resolve_fixup_kernel<true><<<grid, 128, 0, stream>>>(args, list, count);
+	else taa_resolve_fixup_kernel<false><<<grid, 128, 0, stream>>>(args, list, count);
 	return cudaGetLastError();
 }
 

@@ -1,0 +1,475 @@
+// taa_resolve_tuned.cu — the tuned resolve kernel for the BASELINE configs 2-5 family of settings
+// (SURVEY A.8): YCoCg variance clipping, clipAabb rectification, Catmull-Rom history, velocity
+// reprojection, optional outside / depth / anti-ghost rejection, velocity alpha, Lottes weighting,
+// near-clamp anti-flicker. Everything else runs on the exact generic kernel (taa_dispatch.cu decides).
+//
+// Structure (one CTA = 32 x 32 output pixels, 8 warps, each thread owns a 4-pixel column strip):
+//   phase 0  per-tile tables of the sampler coordinates, which depend on the column or the row only
+//   phase 1  the 34 x 34 tile of sampled, YCoCg-converted current colour -> shared memory (each of
+//            the 9 neighbourhood taps of taa.comp:204-212 is the centre tap of some pixel)
+//   phase 2  per pixel: 3x3 moments from shared memory (row sums slide down the strip), velocity
+//            sample, history gather on the 4x4 Catmull-Rom footprint, clip, blend, store
+//
+// Arithmetic contract (this file is compiled with --fmad=false like the rest; fmaf is explicit):
+//   EXACT, in the oracle's operation order: pixel uv, the velocity sample, history uv, every
+//     rejection predicate (taa.comp:789-823) and therefore bit 0 of the mask, the history texel
+//     coordinates and the sampler's sub-texel offsets.
+//   RE-ASSOCIATED / CONTRACTED: colour filtering (neighbourhood moments, history footprint evaluated
+//     with separable weights on 4x4 texels instead of 9 bilinear taps, clip, blend). The sampler's
+//     fp32 coordinate rounding (a tap "at a texel centre" lands up to ~1e-3 texel beside it and bleeds
+//     the neighbour in) is kept for the colour taps and for the dominant centre tap of the history
+//     filter, so the result stays within ~1e-5 of the exact kernel, far inside the 2^-10 gate.
+//   The `rectified` predicate (taa.comp:845, bit 1 of the mask) compares a colour difference with
+//     0.001; pixels where the re-associated value is within FIXUP_BAND_4K (scaled with the frame size) of that threshold are appended
+//     to a list and recomputed by the exact arithmetic in a second, tiny launch (launch_resolve_fixup),
+//     which makes the mask bit-exact.
+#include "taa_device.cuh"
+#include "taa_kernels.h"
+
+namespace taa {
+
+namespace {
+
+constexpr int TW = 32;           // tile width: one warp
+constexpr int NWARP = 8;
+constexpr int RPT = 4;           // rows per thread
+constexpr int TH = NWARP * RPT;  // tile height
+constexpr int SW = TW + 2, SH = TH + 2;
+constexpr int NT = TW * NWARP;
+constexpr int S_ITERS = (SW * SH + NT - 1) / NT;
+// |tuned - exact| of the clip distance is dominated by the two outer Catmull-Rom taps, whose sampler bleed (<= 0.074 * eps * texel
+// contrast, eps <= ~6e-4 texel at x ~ 3840) the 4x4 footprint cannot hold: <= ~2e-5 on full-contrast edges at 4K. The band is twice
+// that and grows with the frame size like eps does.
+constexpr float FIXUP_BAND_4K = 4.0e-5f;
+
+// sampler footprints that depend on the column or on the row only, as byte offsets into the image
+struct ColX { int m, n; float p; };                 // colour tap: main texel, bleeding neighbour (byte offsets in a row), its weight
+struct ColY { long long m, n; float p; int pad; };  // same for rows (byte offsets of the rows in the buffer)
+struct VelX { int o0, o1; float a, u; };            // velocity tap: exact bilinear footprint and the pixel's u (taa.comp:131)
+struct VelY { long long o0, o1; float a, v; };
+
+struct __align__(16) Smem {
+	float4 S[SH][SW];
+	ColY crow[SH];
+	VelY vrow[TH];
+	ColX ccol[SW];
+	VelX vcol[TW];
+	unsigned long long wmask[TH + 4];  // bit c of row r: velocity.w != 0 at texel (x0 - 2 + c, y0 - 2 + r), clamped to the image
+};
+
+__device__ __forceinline__ float sat(float x) { return __saturatef(x); }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ __half2 h2(unsigned int v) { return *reinterpret_cast<__half2*>(&v); }
+
+// byte offset of global row gy in a (band) buffer; rows the buffer does not hold are clamped into it and reported
+template <class I>
+__device__ __forceinline__ long long row_off(const I& im, int gy, unsigned int* status) {
+	int ly = gy - im.y0;
+	if ((unsigned int)ly >= (unsigned int)im.rows) {
+		if (status) atomicOr(status, 1u);
+		ly = ly < 0 ? 0 : im.rows - 1;
+	}
+	return (long long)ly * im.pitch;
+}
+
+// taa.comp:207: offset + vec2(iuv + d + 0.5) * invsize with offset = 0, through the sampler (exact coordinate arithmetic)
+__device__ __forceinline__ void colour_axis(int g, float inv, int size, int& m, int& n, float& p) {
+	Lin L = lin_coord(((float)g + 0.5f) * inv, size);
+	if (L.a < 0.5f) { m = L.i0; n = L.i1; p = L.a; } else { m = L.i1; n = L.i0; p = 1.0f - L.a; }
+}
+
+// One axis of sample_history_bicubic_catmullrom (taa.comp:441-514) as weights on the 4 texels k-1..k+2.
+// The centre tap's sampler position is evaluated exactly as the shader + sampler do, ((tc + w2/wC) * invTexSize) * size - 0.5,
+// and spread with the bilinear tent, so its rounding bleed lands on the right texel. The two outer taps
+// (|w| <= 0.074) are taken at their texel centres.
+struct AxisW { int k; float w[4]; };
+__device__ __forceinline__ AxisW catmull_axis(float h, float size, float inv) {
+	const float it = h * size;                        // iTc = uv * texSize
+	const float kf = floorf(it - 0.5f);
+	const float tc = kf + 0.5f;                       // round down to the nearest texel centre
+	const float f = it - tc;
+	const float f2 = f * f;
+	const float w0 = f * fmaf(f, fmaf(-0.5f, f, 1.0f), -0.5f);
+	const float w1 = fmaf(f2, fmaf(1.5f, f, -2.5f), 1.0f);
+	const float w2 = f * fmaf(f, fmaf(-1.5f, f, 2.0f), 0.5f);
+	const float w3 = f2 * fmaf(0.5f, f, -0.5f);
+	const float wC = w1 + w2;
+	const float r = w2 * rcp_approx(wC);
+	const float uC = ((tc + r) * inv) * size - 0.5f;  // the sampler's unnormalised coordinate of the centre tap
+	const float sC = uC - kf;                         // in [0,1] up to the coordinate rounding
+	const float d1 = sC - 1.0f;
+	AxisW o;
+	o.w[0] = fmaf(wC, sat(-sC), w0);
+	o.w[1] = wC * sat(1.0f - fabsf(sC));
+	o.w[2] = wC * sat(1.0f - fabsf(d1));
+	o.w[3] = fmaf(wC, sat(d1), w3);
+	o.k = (int)fminf(fmaxf(kf, -8.0f), size + 8.0f);  // NaN -> 0; keeps k + 2 far from integer overflow
+	return o;
+}
+
+struct Hist { float r, g, b, a; unsigned int abits; };
+
+// the 4x4 footprint. INTERIOR: no texel is clamped and all rows are in the buffer -> one base pointer, immediate offsets.
+template <bool REJ, bool INTERIOR>
+__device__ __forceinline__ Hist gather_history(const Img& him, const AxisW& ax, const AxisW& ay, int W, int H, unsigned int* st) {
+	Hist o = {0.f, 0.f, 0.f, 0.f, 0u};
+	const unsigned char* base = nullptr;
+	int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+	if (INTERIOR) {
+		base = him.p + (long long)(ay.k - 1 - him.y0) * him.pitch + (long long)(ax.k - 1) * 8;
+	} else {
+		c0 = iclamp(ax.k - 1, 0, W - 1); c1 = iclamp(ax.k, 0, W - 1); c2 = iclamp(ax.k + 1, 0, W - 1); c3 = iclamp(ax.k + 2, 0, W - 1);
+	}
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		uint2 q0, q1, q2, q3;
+		if (INTERIOR) {
+			const uint2* hp = reinterpret_cast<const uint2*>(base + i * him.pitch);
+			q0 = __ldg(hp); q1 = __ldg(hp + 1); q2 = __ldg(hp + 2); q3 = __ldg(hp + 3);
+		} else {
+			const uint2* hp = reinterpret_cast<const uint2*>(him.p + row_off(him, iclamp(ay.k - 1 + i, 0, H - 1), st));
+			q0 = __ldg(hp + c0); q1 = __ldg(hp + c1); q2 = __ldg(hp + c2); q3 = __ldg(hp + c3);
+		}
+		const float2 e0 = __half22float2(h2(q0.x)), e1 = __half22float2(h2(q1.x)), e2 = __half22float2(h2(q2.x)), e3 = __half22float2(h2(q3.x));
+		const float wy = ay.w[i];
+		o.r = fmaf(wy, fmaf(ax.w[3], e3.x, fmaf(ax.w[2], e2.x, fmaf(ax.w[1], e1.x, ax.w[0] * e0.x))), o.r);
+		o.g = fmaf(wy, fmaf(ax.w[3], e3.y, fmaf(ax.w[2], e2.y, fmaf(ax.w[1], e1.y, ax.w[0] * e0.y))), o.g);
+		if (REJ) {
+			const float2 g0 = __half22float2(h2(q0.y)), g1 = __half22float2(h2(q1.y)), g2 = __half22float2(h2(q2.y)), g3 = __half22float2(h2(q3.y));
+			o.b = fmaf(wy, fmaf(ax.w[3], g3.x, fmaf(ax.w[2], g2.x, fmaf(ax.w[1], g1.x, ax.w[0] * g0.x))), o.b);
+			o.a = fmaf(wy, fmaf(ax.w[3], g3.y, fmaf(ax.w[2], g2.y, fmaf(ax.w[1], g1.y, ax.w[0] * g0.y))), o.a);
+			o.abits |= (q0.y | q1.y) | (q2.y | q3.y);
+		} else {
+			const float g0 = __low2float(h2(q0.y)), g1 = __low2float(h2(q1.y)), g2 = __low2float(h2(q2.y)), g3 = __low2float(h2(q3.y));
+			o.b = fmaf(wy, fmaf(ax.w[3], g3, fmaf(ax.w[2], g2, fmaf(ax.w[1], g1, ax.w[0] * g0))), o.b);
+		}
+	}
+	return o;
+}
+
+template <bool REJ, bool ALPHA>
+__global__ void __launch_bounds__(NT, 3)
+taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
+                         unsigned int* __restrict__ fix_count_next, const float fix_band) {
+	__shared__ Smem sm;
+	const TaaParameters& P = A.ubo.param[0];
+	unsigned int* st = A.status;
+	const int W = A.out_w, H = A.out_h;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int x0 = blockIdx.x * TW;
+	const int y0 = A.band_y0 + blockIdx.y * TH;
+	const int rows_valid = min(TH, A.band_y0 + A.band_rows - y0);
+	const float fW = (float)W, fH = (float)H;
+	const float invw = 1.0f / fW, invh = 1.0f / fH;
+
+	if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && fix_count_next) *fix_count_next = 0u;  // the counter the next frame appends to
+
+	// ---- phase 0: coordinate tables ----------------------------------------------------------------
+	if (tid < SW) {
+		ColX t;
+		int m, n;
+		colour_axis(x0 - 1 + tid, invw, W, m, n, t.p);
+		t.m = m * 8; t.n = n * 8;
+		sm.ccol[tid] = t;
+	} else if (tid >= 64 && tid < 64 + rows_valid + 2) {
+		ColY t;
+		int m, n;
+		colour_axis(y0 - 1 + (tid - 64), invh, H, m, n, t.p);
+		t.m = row_off(A.color, m, st); t.n = row_off(A.color, n, st); t.pad = 0;
+		sm.crow[tid - 64] = t;
+	} else if (tid >= 128 && tid < 128 + TW) {
+		const int x = min(x0 + (tid - 128), W - 1);
+		const float u = ((float)x + 0.5f) / fW;  // tc_to_uv, taa.comp:131
+		Lin L = lin_coord(u, W);
+		VelX t = {L.i0 * 8, L.i1 * 8, L.a, u};
+		sm.vcol[tid - 128] = t;
+	} else if (tid >= 192 && tid < 192 + rows_valid) {
+		const int y = y0 + (tid - 192);
+		const float v = ((float)y + 0.5f) / fH;
+		Lin L = lin_coord(v, H);
+		VelY t = {row_off(A.velocity, L.i0, st), row_off(A.velocity, L.i1, st), L.a, v};
+		sm.vrow[tid - 192] = t;
+	}
+	// Movers (velocity.w != 0, fwd_geometry.frag:289-295) are what the 5-tap anti-ghosting test looks for (taa.comp:796-811). Every tap's
+	// bilinear footprint lies inside the 5x5 texels around the pixel; where all of them have w == +-0 the taps return w == 0 exactly.
+	if (REJ && P.mDynamicAntiGhosting) {
+		for (int r = warp; r < rows_valid + 4; r += NWARP) {
+			const uint2* vp = reinterpret_cast<const uint2*>(A.velocity.p + row_off(A.velocity, iclamp(y0 - 2 + r, 0, H - 1), st));
+			const unsigned int wa = __ldg(vp + iclamp(x0 - 2 + lane, 0, W - 1)).y & 0x7fff0000u;
+			const unsigned int wb = lane < 4 ? (__ldg(vp + iclamp(x0 + 30 + lane, 0, W - 1)).y & 0x7fff0000u) : 0u;
+			const unsigned int lo = __ballot_sync(0xffffffffu, wa != 0u), hi = __ballot_sync(0xffffffffu, wb != 0u);
+			if (lane == 0) sm.wmask[r] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+		}
+	}
+	__syncthreads();
+
+	// ---- phase 1: sampled current colour in YCoCg --------------------------------------------------
+	// S = T[m] + px (T[nx] - T[m]) + py (T[ny] - T[m]); the corrections are ~1e-4 of a texel difference and are
+	// evaluated in packed fp16 (their own rounding error is below 1e-7); the px*py cross term (< 1e-6) is dropped.
+	{
+		const int n_s = (rows_valid + 2) * SW;
+		uint2 M[S_ITERS], NX[S_ITERS], NY[S_ITERS];
+		float pxs[S_ITERS], pys[S_ITERS];
+#pragma unroll
+		for (int k = 0; k < S_ITERS; ++k) {
+			const int idx = min(tid + k * NT, n_s - 1);
+			const int r = idx / SW, c = idx - r * SW;
+			const ColX cx = sm.ccol[c];
+			const ColY cy = sm.crow[r];
+			const unsigned char* rm = A.color.p + cy.m;
+			M[k] = __ldg(reinterpret_cast<const uint2*>(rm + cx.m));
+			NX[k] = __ldg(reinterpret_cast<const uint2*>(rm + cx.n));
+			NY[k] = __ldg(reinterpret_cast<const uint2*>(A.color.p + cy.n + cx.m));
+			pxs[k] = cx.p; pys[k] = cy.p;
+		}
+#pragma unroll
+		for (int k = 0; k < S_ITERS; ++k) {
+			const int idx = tid + k * NT;
+			if (idx < n_s) {
+				const int r = idx / SW, c = idx - r * SW;
+				const __half2 px = __float2half2_rn(pxs[k]), py = __float2half2_rn(pys[k]);
+				const __half2 m01 = h2(M[k].x), m23 = h2(M[k].y);
+				const __half2 c01 = __hfma2(px, __hsub2(h2(NX[k].x), m01), __hmul2(py, __hsub2(h2(NY[k].x), m01)));
+				const __half2 c23 = __hfma2(px, __hsub2(h2(NX[k].y), m23), __hmul2(py, __hsub2(h2(NY[k].y), m23)));
+				const float2 a01 = __half22float2(m01), b01 = __half22float2(c01);
+				const float cr = a01.x + b01.x, cg = a01.y + b01.y, cb = __low2float(m23) + __low2float(c23);
+				const float t = cr + cb, hg = 0.5f * cg;
+				sm.S[r][c] = make_float4(fmaf(0.25f, t, hg), 0.5f * (cr - cb), fmaf(-0.25f, t, hg), 0.0f);
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---- phase 2: one column strip per thread ------------------------------------------------------
+	const int x = x0 + lane;
+	const bool xvalid = x < W;
+	const VelX vc = sm.vcol[lane];
+	const float u = vc.u;
+	const int r0 = warp * RPT;
+	if (r0 >= rows_valid) return;
+
+	// history rows this buffer holds, for the interior test of the gather
+	const int hlo = max(0, A.history_in.y0), hhi = min(H - 1, A.history_in.y0 + A.history_in.rows - 1);
+	// output pointers of this thread's column, walking down the strip
+	const int xs = min(x, W - 1);
+	unsigned char* p_hist = A.history_out.p + (long long)(y0 + r0 - A.history_out.y0) * A.history_out.pitch + (long long)xs * 8;
+	unsigned char* p_res = A.result.p ? A.result.p + (long long)(y0 + r0 - A.result.y0) * A.result.pitch + (long long)xs * 8 : nullptr;
+	unsigned char* p_mask = A.mask.p ? A.mask.p + (long long)(y0 + r0 - A.mask.y0) * A.mask.pitch + (long long)xs * 4 : nullptr;
+	const unsigned char* p_depth = nullptr;
+	if (REJ) p_depth = A.depth.p + row_off(A.depth, y0 + r0, st) + (long long)xs * 4;
+
+	// row sums of the first two neighbourhood rows of the strip
+	float3 s1a, s2a, s1b, s2b, cur_next;
+	{
+		const float4 a = sm.S[r0][lane], b = sm.S[r0][lane + 1], c = sm.S[r0][lane + 2];
+		s1a = make_float3(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z);
+		s2a = make_float3(fmaf(a.x, a.x, fmaf(b.x, b.x, c.x * c.x)), fmaf(a.y, a.y, fmaf(b.y, b.y, c.y * c.y)), fmaf(a.z, a.z, fmaf(b.z, b.z, c.z * c.z)));
+	}
+	{
+		const float4 a = sm.S[r0 + 1][lane], b = sm.S[r0 + 1][lane + 1], c = sm.S[r0 + 1][lane + 2];
+		s1b = make_float3(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z);
+		s2b = make_float3(fmaf(a.x, a.x, fmaf(b.x, b.x, c.x * c.x)), fmaf(a.y, a.y, fmaf(b.y, b.y, c.y * c.y)), fmaf(a.z, a.z, fmaf(b.z, b.z, c.z * c.z)));
+		cur_next = make_float3(b.x, b.y, b.z);
+	}
+
+#pragma unroll
+	for (int rr = 0; rr < RPT; ++rr) {
+		const int rt = r0 + rr;  // tile row of this pixel
+		if (rt >= rows_valid) break;
+		const int y = y0 + rt;
+		const float3 cur = cur_next;
+		float3 s1c, s2c;
+		{
+			const float4 a = sm.S[rt + 2][lane], b = sm.S[rt + 2][lane + 1], c = sm.S[rt + 2][lane + 2];
+			s1c = make_float3(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z);
+			s2c = make_float3(fmaf(a.x, a.x, fmaf(b.x, b.x, c.x * c.x)), fmaf(a.y, a.y, fmaf(b.y, b.y, c.y * c.y)), fmaf(a.z, a.z, fmaf(b.z, b.z, c.z * c.z)));
+			cur_next = make_float3(b.x, b.y, b.z);
+		}
+		// ---- variance box (taa.comp:266-277) ----
+		const float ninth = 1.0f / 9.0f;
+		const float3 mean = make_float3((s1a.x + s1b.x + s1c.x) * ninth, (s1a.y + s1b.y + s1c.y) * ninth, (s1a.z + s1b.z + s1c.z) * ninth);
+		const float3 msq = make_float3((s2a.x + s2b.x + s2c.x) * ninth, (s2a.y + s2b.y + s2c.y) * ninth, (s2a.z + s2b.z + s2c.z) * ninth);
+		const float g = P.mVarClipGamma;
+		const float3 ext = make_float3(g * sqrt_approx(fmaxf(0.f, fmaf(-mean.x, mean.x, msq.x))), g * sqrt_approx(fmaxf(0.f, fmaf(-mean.y, mean.y, msq.y))),
+		                               g * sqrt_approx(fmaxf(0.f, fmaf(-mean.z, mean.z, msq.z))));
+		s1a = s1b; s2a = s2b; s1b = s1c; s2b = s2c;
+
+		// ---- getHistoryPosition (taa.comp:391-438), exact ----
+		const VelY vr = sm.vrow[rt];
+		const float v = vr.v;
+		float velx, vely, velz = 0.f;
+		bool movC = false;
+		{
+			const unsigned char* p0 = A.velocity.p + vr.o0;
+			const unsigned char* p1 = A.velocity.p + vr.o1;
+			const uint2 t00 = __ldg(reinterpret_cast<const uint2*>(p0 + vc.o0)), t10 = __ldg(reinterpret_cast<const uint2*>(p0 + vc.o1));
+			const uint2 t01 = __ldg(reinterpret_cast<const uint2*>(p1 + vc.o0)), t11 = __ldg(reinterpret_cast<const uint2*>(p1 + vc.o1));
+			const float2 a00 = __half22float2(h2(t00.x)), a10 = __half22float2(h2(t10.x)), a01 = __half22float2(h2(t01.x)), a11 = __half22float2(h2(t11.x));
+			velx = lerpf(lerpf(a00.x, a10.x, vc.a), lerpf(a01.x, a11.x, vc.a), vr.a);
+			vely = lerpf(lerpf(a00.y, a10.y, vc.a), lerpf(a01.y, a11.y, vc.a), vr.a);
+			if (REJ) {
+				const float2 b00 = __half22float2(h2(t00.y)), b10 = __half22float2(h2(t10.y)), b01 = __half22float2(h2(t01.y)), b11 = __half22float2(h2(t11.y));
+				velz = lerpf(lerpf(b00.x, b10.x, vc.a), lerpf(b01.x, b11.x, vc.a), vr.a);
+				const float velw = lerpf(lerpf(b00.y, b10.y, vc.a), lerpf(b01.y, b11.y, vc.a), vr.a);
+				movC = (fabsf(velx) > 1e-5f || fabsf(vely) > 1e-5f) && (fabsf(velw) >= 0.5f);
+			}
+		}
+		const float hu = u - velx, hv = v - vely;
+
+		// ---- history: 4x4 Catmull-Rom footprint with separable weights ----
+		const AxisW ax = catmull_axis(hu, fW, invw), ay = catmull_axis(hv, fH, invh);
+		const bool interior = (unsigned int)(ax.k - 1) <= (unsigned int)(W - 4) && ay.k - 1 >= hlo && ay.k + 2 <= hhi;
+		const Hist hs = interior ? gather_history<REJ, true>(A.history_in, ax, ay, W, H, st) : gather_history<REJ, false>(A.history_in, ax, ay, W, H, st);
+		float3 hist;  // maybe_rgb_to_ycocg(historyRaw.rgb), taa.comp:769
+		{
+			const float t = hs.r + hs.b, hg2 = 0.5f * hs.g;
+			hist = make_float3(fmaf(0.25f, t, hg2), 0.5f * (hs.r - hs.b), fmaf(-0.25f, t, hg2));
+		}
+
+		// ---- rejection (taa.comp:787-823), exact predicates ----
+		bool rejected = false, uncertain = false;
+		float writeDynamicMask = 0.f;
+		if (REJ) {
+			if (P.mRejectOutside && (hu < 0.f || hv < 0.f || hu >= 1.f || hv >= 1.f)) rejected = true;
+			if (P.mDynamicAntiGhosting) {
+				auto mov = [&](float s, float t) {
+					float4 q = tex_rgba16f(A.velocity, W, H, s, t, st);
+					return (fabsf(q.x) > 1e-5f || fabsf(q.y) > 1e-5f) && (fabsf(q.w) >= 0.5f);
+				};
+				bool movement = movC;
+				const unsigned long long near_movers = ((sm.wmask[rt] | sm.wmask[rt + 1] | sm.wmask[rt + 2] | sm.wmask[rt + 3] | sm.wmask[rt + 4]) >> lane) & 0x1full;
+				if (!movement && near_movers) movement = mov(u + invw * -1.f, v + invh * 0.f) || mov(u + invw * 1.f, v + invh * 0.f) ||
+				                                         mov(u + invw * 0.f, v + invh * -1.f) || mov(u + invw * 0.f, v + invh * 1.f);
+				if (!movement) {
+					if (hs.a > 0.0f) rejected = true;
+					if ((hs.abits & 0x7fff0000u) != 0u) {
+						// the sign of a filtered 0/1 mask that cancels to ~0 is not safe under re-association
+						if (fabsf(hs.a) < 2.5f * fix_band) uncertain = true;
+					} else {
+						// all 16 texels carry alpha == 0, so hs.a == 0 exactly; the exact 9-tap sum can still be != 0 when an outer
+						// tap's sampler bleed reaches a texel of the 6x6 ring with alpha != 0
+						unsigned int ring = 0x7fff0000u;
+						if ((unsigned int)(ax.k - 2) <= (unsigned int)(W - 6) && ay.k - 2 >= hlo && ay.k + 3 <= hhi) {
+							const unsigned char* rb = A.history_in.p + (long long)(ay.k - 2 - A.history_in.y0) * A.history_in.pitch + (long long)(ax.k - 2) * 8 + 4;
+							const long long hp = A.history_in.pitch;
+							ring = 0u;
+#pragma unroll
+							for (int j = 0; j < 6; ++j) ring |= __ldg(reinterpret_cast<const unsigned int*>(rb + j * 8)) | __ldg(reinterpret_cast<const unsigned int*>(rb + 5 * hp + j * 8));
+#pragma unroll
+							for (int i = 1; i < 5; ++i) ring |= __ldg(reinterpret_cast<const unsigned int*>(rb + i * hp)) | __ldg(reinterpret_cast<const unsigned int*>(rb + i * hp + 40));
+						}
+						if (ring & 0x7fff0000u) uncertain = true;
+					}
+				}
+				writeDynamicMask = movC ? 1.0f : 0.0f;
+			}
+			if (P.mDepthCulling) {
+				const float depth = __ldg(reinterpret_cast<const float*>(p_depth));
+				const float expected = depth - velz;
+				const int tx = (int)(hu * fW), ty = (int)(hv * fH);
+				const float hd = fetch_r32f(A.history_depth, W, H, tx, ty, st);
+				if (fabsf(hd - expected) > 0.1f * (1.0f - hd)) rejected = true;
+			}
+			p_depth += A.depth.pitch;
+		}
+
+		// ---- clipAabb towards the box centre (taa.comp:323-345) ----
+		const float3 vcl = make_float3(hist.x - mean.x, hist.y - mean.y, hist.z - mean.z);
+		const float ma = fmaxf(fabsf(vcl.x) * rcp_approx(ext.x + 1e-7f), fmaxf(fabsf(vcl.y) * rcp_approx(ext.y + 1e-7f), fabsf(vcl.z) * rcp_approx(ext.z + 1e-7f)));
+		float3 hc = hist;
+		bool rectified = false;
+		if (ma > 1.0f) {
+			const float s = rcp_approx(ma);
+			hc = make_float3(fmaf(vcl.x, s, mean.x), fmaf(vcl.y, s, mean.y), fmaf(vcl.z, s, mean.z));
+			const float dx = fabsf(hc.x - hist.x), dy = fabsf(hc.y - hist.y), dz = fabsf(hc.z - hist.z);
+			rectified = fmaxf(dx, fmaxf(dy, dz)) > 0.001f;
+			if (fminf(fabsf(dx - 0.001f), fminf(fabsf(dy - 0.001f), fabsf(dz - 0.001f))) < fix_band) uncertain = true;
+		}
+
+		// ---- blend (taa.comp:848-900) ----
+		float alpha = P.mAlpha;
+		if (rejected) {
+			alpha = P.mRejectionAlpha;
+		} else if (ALPHA) {
+			if (P.mVelBasedAlpha) {
+				const float du = u - hu, dv = v - hv;
+				const float speed = sqrt_approx(fmaf(du, du, dv * dv));
+				alpha = fmaxf(alpha, mixf(alpha, P.mVelBasedAlphaMax, sat(speed * P.mVelBasedAlphaFactor)));
+			}
+			if (P.mLumaWeightingLottes) {
+				const float lc = cur.x, lh = hc.x;
+				const float w = 1.0f - fabsf(lc - lh) * rcp_approx(fmaxf(fmaxf(lc, lh), 0.2f));
+				alpha = mixf(P.mMaxAlpha, P.mMinAlpha, w * w);
+			}
+			if (P.mReduceBlendNearClamp) {
+				const float lmin = mean.x - ext.x, lmax = mean.x + ext.x, lh = hist.x;
+				float dist = 2.0f * fabsf(fminf(lh - lmin, lmax - lh)) * rcp_approx(lmax - lmin);
+				if (lmax - lmin < 0.001f) dist = 1.0f;
+				alpha *= sat(4.0f * dist);
+			}
+		}
+		if (A.ubo.mResetHistory) alpha = 1.0f;
+		const float om = 1.0f - alpha;
+		const float oy = fmaf(hc.x, om, cur.x * alpha), oco = fmaf(hc.y, om, cur.y * alpha), ocg = fmaf(hc.z, om, cur.z * alpha);
+		const float tmp = oy - ocg;
+		const float outr = tmp + oco, outg = oy + ocg, outb = tmp - oco;
+
+		// ---- stores (taa.comp:908-909, 955-956) ----
+		if (xvalid) {
+			const __half2 rg = __floats2half2_rn(outr, outg);
+			const __half2 bm = __floats2half2_rn(outb, writeDynamicMask), b1 = __floats2half2_rn(outb, 1.0f);
+			*reinterpret_cast<uint2*>(p_hist) = make_uint2(*reinterpret_cast<const unsigned int*>(&rg), *reinterpret_cast<const unsigned int*>(&bm));
+			if (p_res) *reinterpret_cast<uint2*>(p_res) = make_uint2(*reinterpret_cast<const unsigned int*>(&rg), *reinterpret_cast<const unsigned int*>(&b1));
+			if (p_mask) *reinterpret_cast<unsigned int*>(p_mask) = (rejected ? 1u : 0u) | (rectified ? 2u : 0u) | (2u << 2);
+		}
+		p_hist += A.history_out.pitch;
+		if (p_res) p_res += A.result.pitch;
+		if (p_mask) p_mask += A.mask.pitch;
+
+		// ---- hand the undecidable pixels to the exact pass (one atomic per warp) ----
+		const unsigned int um = __ballot_sync(0xffffffffu, uncertain && xvalid && fix_list != nullptr);
+		if (um) {
+			const int leader = __ffs(um) - 1;
+			unsigned int slot = 0;
+			if (lane == leader) slot = atomicAdd(fix_count, (unsigned int)__popc(um));
+			slot = __shfl_sync(0xffffffffu, slot, leader);
+			if ((um >> lane) & 1u) fix_list[slot + __popc(um & ((1u << lane) - 1u))] = (unsigned int)y * (unsigned int)W + (unsigned int)x;
+		}
+	}
+}
+
+}  // namespace
+
+bool tuned_supports(const ResolveArgs& A) {
+	const TaaUniforms& U = A.ubo;
+	const TaaParameters& P = U.param[0];
+	if (U.splitScreen || U.mUpsampling || U.mBypassHistoryUpdate) return false;
+	if (A.in_w != A.out_w || A.in_h != A.out_h) return false;
+	if ((long long)A.out_w * A.out_h >= (1ll << 32)) return false;
+	if (A.debug.p || A.segmask.p) return false;
+	if (P.mPassThrough || !P.mUseYCoCg || P.mShrinkChromaAxis || !P.mVarianceClipping || P.mColorClampingOrClipping != 2) return false;
+	if (P.mUnjitterNeighbourhood || P.mUnjitterCurrentSample || P.mToneMapLumaKaris || P.mAddNoise || P.mRayTraceAugment) return false;
+	if (P.mUseVelocityVectors != 2 || P.mVelocitySampleMode != 0 || P.mInterpolationMode != 2) return false;
+	if (P.mDepthCulling && !A.history_depth.p) return false;
+	return true;
+}
+
+cudaError_t launch_resolve_tuned(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, cudaStream_t stream) {
+	const TaaParameters& P = A.ubo.param[0];
+	const float band = FIXUP_BAND_4K * fmaxf(1.0f, fmaxf((float)A.out_w / 3840.0f, (float)A.out_h / 3840.0f));
+	const bool rej = P.mDepthCulling || P.mRejectOutside || P.mDynamicAntiGhosting;
+	const bool alp = P.mVelBasedAlpha || P.mLumaWeightingLottes || P.mReduceBlendNearClamp;
+	dim3 block(TW * NWARP);
+	dim3 grid((A.out_w + TW - 1) / TW, (A.band_rows + TH - 1) / TH);
+	if (rej) {
+		if (alp) taa_resolve_tuned_kernel<true, true><<<grid, block, 0, stream>>>(A, fix_list, fix_count, fix_count_next, band);
+		else taa_resolve_tuned_kernel<true, false><<<grid, block, 0, stream>>>(A, fix_list, fix_count, fix_count_next, band);
+	} else {
+		if (alp) taa_resolve_tuned_kernel<false, true><<<grid, block, 0, stream>>>(A, fix_list, fix_count, fix_count_next, band);
+		else taa_resolve_tuned_kernel<false, false><<<grid, block, 0, stream>>>(A, fix_list, fix_count, fix_count_next, band);
+	}
+	return cudaGetLastError();
+}
+
+}  // namespace taa

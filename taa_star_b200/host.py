@@ -122,6 +122,10 @@ class TaaContext:
     def poll_status(self, stream=None) -> int:
         return self._lib.taa_poll_status(self._h, _stream_ptr(stream))
 
+    def fixup_pixels(self, stream=None) -> int:
+        """Pixels the last resolve handed from the tuned kernel to the exact fix-up pass (synchronises)."""
+        return int(self._lib.taa_fixup_pixels(self._h, _stream_ptr(stream)))
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.taa_launch_count(self._h))

@@ -181,7 +181,7 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
     W, H = (7680, 4320) if (args.width, args.height) == (3840, 2160) else (args.width, args.height)
     cfg_id = args.config
     p = configs.config2_resolve() if cfg_id == 2 else configs.config3_full_chain()
-    flags = abi.TAA_FLAG_FAST_FILTER if args.fast else 0
+    flags = abi.TAA_FLAG_EXACT if args.exact else 0
     halo = 20  # |v_y| <= 16 px guaranteed by the generator + 2 filter + 2 guard
     sh = ShardedTaa(W, H, halo=halo, flags=flags, device=dev, apron=halo if cfg_id == 3 else 2)
     L = sh.L

@@ -1,7 +1,8 @@
 """GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
 
 Bar (BASELINE.json north_star): rgba16f outputs within 2^-10 per channel per frame, PSNR >= 60 dB after 64 accumulated
-frames, integer masks bit-exact. The EXACT kernels are held to a stricter bar here: bit-identical fp16 outputs.
+frames, integer masks bit-exact. The EXACT kernels are held to a stricter bar here: bit-identical fp16 outputs
+(contexts are created with TAA_FLAG_EXACT). The default (tuned) path is tested in test_tuned_gpu.py.
 """
 import ctypes as C
 
@@ -22,7 +23,7 @@ def scene(w=W, h=H, **kw):
     return SyntheticScene(w, h, **kw)
 
 
-def check_exact(oracle, u, ins, hist, out_size=None, want=("history_out", "result", "mask"), flags=0, hist_depth=None, prev_matid=None,
+def check_exact(oracle, u, ins, hist, out_size=None, want=("history_out", "result", "mask"), flags=abi.TAA_FLAG_EXACT, hist_depth=None, prev_matid=None,
                 prev_segmask=None, tol=None, ctx=None):
     in_h, in_w = ins["depth"].shape
     ref = oracle.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=hist_depth, prev_segmask=prev_segmask,
@@ -205,7 +206,7 @@ def test_segmentation_mask(oracle):
     u = configs.uniforms_for(p, f1.jitter_ndc)
     ref = oracle.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=f0.depth.numpy(), matid=ins["matid"],
                          uvnrm=ins["uvnrm"], want=("segmask",))
-    ctx = host.TaaContext((W, H))
+    ctx = host.TaaContext((W, H), flags=abi.TAA_FLAG_EXACT)
     got = run_gpu_resolve(ctx, u, ins, hist, hist_depth=f0.depth.numpy(), want=("segmask", "history_out"))
     assert (ref["segmask"] != got["segmask"]).mean() < 1e-3
     assert 0.01 < (ref["segmask"] != 0).mean() < 0.99
@@ -218,7 +219,7 @@ def test_64_frame_sequence(oracle, cfg):
     w, h = 192, 108
     sc = scene(w, h)
     p = {"config2": configs.config2_resolve, "config3": configs.config3_full_chain}[cfg]()
-    ctx = host.TaaContext((w, h))
+    ctx = host.TaaContext((w, h), flags=abi.TAA_FLAG_EXACT)
     hist_ref = np.zeros((h, w, 4), np.float16)
     hist_gpu = hist_ref.copy()
     prev_depth = None
@@ -248,7 +249,7 @@ def test_converges_to_supersampled_reference(oracle):
     w, h = 160, 90
     sc = scene(w, h, pan_px=(0.0, 0.0), mover_px=(0.0, 0.0))
     p = configs.config2_resolve()
-    ctx = host.TaaContext((w, h))
+    ctx = host.TaaContext((w, h), flags=abi.TAA_FLAG_EXACT)
     hist = np.zeros((h, w, 4), np.float16)
     frames = [sc.frame(n) for n in range(48)]
     mean = np.mean([f.color.numpy().astype(np.float32) for f in frames[:8]], axis=0)
@@ -269,7 +270,7 @@ def test_taa_resolve_simple_signature(oracle):
     hist = random_history(H, W, 21)
     u = configs.uniforms_for(configs.config2_resolve(), f1.jitter_ndc)
     ref = oracle.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, want=("history_out",))
-    ctx = host.TaaContext((W, H))
+    ctx = host.TaaContext((W, H), flags=abi.TAA_FLAG_EXACT)
     out = torch.zeros(H, W, 4, dtype=torch.float16, device="cuda")
     ctx.resolve_simple(to_dev(ins["color"]), to_dev(ins["depth"]), to_dev(ins["velocity"]), to_dev(hist), out, u)
     torch.cuda.synchronize()
@@ -316,7 +317,7 @@ def test_pitched_images(oracle):
         big[:, :t.shape[1]] = t
         return big[:, :t.shape[1]]
 
-    ctx = host.TaaContext((W, H))
+    ctx = host.TaaContext((W, H), flags=abi.TAA_FLAG_EXACT)
     ho = padded(np.zeros((H, W, 4), np.float16), 3)
     res = padded(np.zeros((H, W, 4), np.float16), 16)
     ctx.resolve(u, color=padded(ins["color"], 5), depth=padded(ins["depth"], 9), velocity=padded(ins["velocity"], 1), history_in=padded(hist, 2),
@@ -339,7 +340,7 @@ def test_row_bands_equal_whole_frame(oracle, nbands):
     rows = [(b * H // nbands, (b + 1) * H // nbands) for b in range(nbands)]
     for (y0, y1) in rows:
         a, b = max(0, y0 - halo), min(H, y1 + halo)
-        ctx = host.TaaContext((W, H), band=(y0, y1 - y0))
+        ctx = host.TaaContext((W, H), band=(y0, y1 - y0), flags=abi.TAA_FLAG_EXACT)
         out = {k: torch.zeros(y1 - y0, W, 4, dtype=torch.float16, device="cuda") for k in ("history_out", "result")}
         mask = torch.zeros(y1 - y0, W, dtype=torch.int32, device="cuda")
         sl = lambda arr: (to_dev(arr[a:b]), a)
@@ -359,7 +360,7 @@ def test_band_halo_overflow_is_reported():
     hist = random_history(H, W, 13)
     u = configs.uniforms_for(configs.config2_resolve(), f1.jitter_ndc)
     y0, y1, halo = 48, 96, 4
-    ctx = host.TaaContext((W, H), band=(y0, y1 - y0))
+    ctx = host.TaaContext((W, H), band=(y0, y1 - y0), flags=abi.TAA_FLAG_EXACT)
     a, b = y0 - halo, y1 + halo
     sl = lambda arr: (to_dev(arr[a:b]), a)
     out = torch.zeros(y1 - y0, W, 4, dtype=torch.float16, device="cuda")

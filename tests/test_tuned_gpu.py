@@ -1,0 +1,266 @@
+"""GPU parity of the DEFAULT path: the tuned shared-memory kernel + exact fix-up pass (taa_resolve_tuned.cu) against the CPU oracle.
+
+Bar (BASELINE.json north_star): every rgba16f output within 2^-10 per channel per frame (same inputs, same history on both
+sides), PSNR >= 60 dB after 64 free-running frames, integer masks bit-exact. Full-size (3840x2160 and a 15360-wide strip) checks
+use the exact GPU kernel — itself bit-identical to the oracle (test_parity_gpu.py) — as the reference, plus oracle row samples.
+"""
+import numpy as np
+import pytest
+import torch
+
+from common import PSNR_MIN, TOL_ABS, np_inputs, psnr, random_history, run_gpu_resolve, to_dev
+from taa_star_b200 import abi, configs, host
+from taa_star_b200.synth import SyntheticScene
+
+pytestmark = pytest.mark.gpu
+
+W, H = 256, 144
+CFG = {"config2": configs.config2_resolve, "config3": configs.config3_full_chain}
+
+
+def with_params(base, **kw):
+    p = abi.TaaParameters.from_buffer_copy(base)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def max_abs_nan_aware(a, b):
+    fa, fb = a.astype(np.float32), b.astype(np.float32)
+    both_nan = np.isnan(fa) & np.isnan(fb)
+    both_same_inf = np.isinf(fa) & (fa == fb)
+    d = np.abs(fa - fb)
+    d[both_nan | both_same_inf] = 0.0
+    return float(np.nan_to_num(d, nan=np.inf).max())
+
+
+def check_tuned(oracle, u, ins, hist, hist_depth=None, ctx=None, want=("history_out", "result", "mask"), expect_tuned=True):
+    in_h, in_w = ins["depth"].shape
+    ref = oracle.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=hist_depth, want=want)
+    own = ctx is None
+    if own:
+        ctx = host.TaaContext((in_w, in_h))
+    n0 = ctx.launch_count
+    got = run_gpu_resolve(ctx, u, ins, hist, hist_depth=hist_depth, want=want)
+    launches = ctx.launch_count - n0
+    assert launches == (2 if expect_tuned else 1), f"{launches} launches: the {'tuned' if expect_tuned else 'general'} path was expected"
+    fix = ctx.fixup_pixels()
+    if own:
+        ctx.close()
+    worst = 0.0
+    for name in want:
+        if name == "mask":
+            bad = int((ref[name] != got[name]).sum())
+            assert bad == 0, f"mask: {bad} of {ref[name].size} values differ (fix-up list held {fix} pixels)"
+        else:
+            d = max_abs_nan_aware(ref[name], got[name])
+            worst = max(worst, d)
+            assert d <= TOL_ABS, f"{name}: max |d| = {d} > 2^-10"
+    return ref, got, worst, fix
+
+
+@pytest.mark.parametrize("cfg", ["config2", "config3"])
+def test_single_frame(oracle, cfg):
+    sc = SyntheticScene(W, H)
+    f0, f1 = sc.frame(4), sc.frame(5)
+    u = configs.uniforms_for(CFG[cfg](), f1.jitter_ndc)
+    for seed in (7, 8):
+        check_tuned(oracle, u, np_inputs(f1), random_history(H, W, seed), hist_depth=f0.depth.numpy())
+
+
+SWITCHES = [dict(mAlpha=0.3), dict(mVarClipGamma=0.75), dict(mVarClipGamma=1.5), dict(mRejectOutside=1), dict(mRejectOutside=1, mRejectionAlpha=0.5),
+            dict(mDepthCulling=1), dict(mDynamicAntiGhosting=1), dict(mVelBasedAlpha=1, mVelBasedAlphaFactor=40.0), dict(mLumaWeightingLottes=1),
+            dict(mReduceBlendNearClamp=1), dict(mReduceBlendNearClamp=1, mLumaWeightingLottes=1, mDepthCulling=1)]
+
+
+@pytest.mark.parametrize("sw", SWITCHES, ids=lambda s: ",".join(f"{k}={v}" for k, v in s.items()))
+def test_each_switch_of_the_family(oracle, sw):
+    sc = SyntheticScene(W, H, pan_px=(5.25, -2.5))
+    f0, f1 = sc.frame(2), sc.frame(3)
+    u = configs.uniforms_for(with_params(configs.config2_resolve(), **sw), f1.jitter_ndc)
+    check_tuned(oracle, u, np_inputs(f1), random_history(H, W, 11), hist_depth=f0.depth.numpy())
+
+
+def test_reset_history(oracle):
+    sc = SyntheticScene(W, H)
+    f1 = sc.frame(1)
+    u = configs.uniforms_for(configs.config2_resolve(), f1.jitter_ndc, reset_history=True)
+    check_tuned(oracle, u, np_inputs(f1), random_history(H, W, 3))
+
+
+@pytest.mark.parametrize("sw", [dict(mInterpolationMode=1), dict(mUseYCoCg=0), dict(mColorClampingOrClipping=1), dict(mUseVelocityVectors=1),
+                                dict(mToneMapLumaKaris=1), dict(mVelocitySampleMode=2), dict(mUnjitterNeighbourhood=1)],
+                         ids=lambda s: ",".join(f"{k}={v}" for k, v in s.items()))
+def test_settings_outside_the_family_run_on_the_general_kernel(oracle, sw):
+    sc = SyntheticScene(W, H)
+    f1 = sc.frame(2)
+    u = configs.uniforms_for(with_params(configs.config2_resolve(), **sw), f1.jitter_ndc)
+    _, _, worst, _ = check_tuned(oracle, u, np_inputs(f1), random_history(H, W, 5), expect_tuned=False)
+    assert worst == 0.0
+
+
+@pytest.mark.parametrize("size", [(1, 1), (2, 3), (17, 5), (31, 33), (33, 31), (130, 9), (300, 70)])
+def test_tiny_and_ragged_sizes(oracle, size):
+    w, h = size
+    sc = SyntheticScene(w, h)
+    f1 = sc.frame(1)
+    for p in (configs.config2_resolve(), configs.config3_full_chain()):
+        u = configs.uniforms_for(p, f1.jitter_ndc)
+        check_tuned(oracle, u, np_inputs(f1), random_history(h, w, 1), hist_depth=f1.depth.numpy())
+
+
+def test_extreme_and_non_finite_motion(oracle):
+    sc = SyntheticScene(W, H, pan_px=(0.0, 0.0))
+    f1 = sc.frame(1)
+    ins = np_inputs(f1)
+    vel = ins["velocity"].astype(np.float32)
+    rng = np.random.default_rng(5)
+    vel[..., 0] = rng.uniform(-1.5, 1.5, (H, W))
+    vel[..., 1] = rng.uniform(-1.5, 1.5, (H, W))
+    vel[0:4, :, 0:2] = 0.0
+    vel[4:8, :, 0] = rng.uniform(-3, 3, (4, W)) / W   # a few pixels of motion, sub-pixel phases everywhere
+    vel[4:8, :, 1] = rng.uniform(-3, 3, (4, W)) / H
+    vel[10, :, 0] = 60000.0
+    vel[11, :, 1] = -60000.0
+    ins["velocity"] = vel.astype(np.float16)
+    ins["velocity"].view(np.uint16)[12, 0:8, 0] = 0x7e00   # NaN
+    ins["velocity"].view(np.uint16)[12, 8:16, 1] = 0x7c00  # +inf
+    ins["velocity"].view(np.uint16)[12, 16:24, 0] = 0xfc00  # -inf
+    hist = random_history(H, W, 9)
+    for p in (configs.config2_resolve(), configs.config3_full_chain()):
+        u = configs.uniforms_for(p, f1.jitter_ndc)
+        check_tuned(oracle, u, ins, hist, hist_depth=f1.depth.numpy())
+
+
+def test_static_camera_subtexel_bleed(oracle):
+    """Zero motion puts every history tap on a texel centre (f ~ 0 or ~ 1), where the sampler's coordinate rounding decides which neighbour
+    bleeds in; a wide frame makes that rounding large (SURVEY 'sampler-exact semantics')."""
+    w, h = 4000, 24
+    sc = SyntheticScene(w, h, pan_px=(0.0, 0.0), mover_px=(0.0, 0.0))
+    f1 = sc.frame(3)
+    u = configs.uniforms_for(configs.config2_resolve(), f1.jitter_ndc)
+    check_tuned(oracle, u, np_inputs(f1), random_history(h, w, 2))
+
+
+@pytest.mark.parametrize("cfg", ["config2", "config3"])
+def test_64_frame_sequence(oracle, cfg):
+    """Per frame: same inputs and same history on both sides -> within 2^-10, masks bit-exact. Free-running on the GPU beside a free-running
+    oracle: PSNR >= 60 dB after 64 accumulated frames."""
+    w, h = 192, 108
+    sc = SyntheticScene(w, h)
+    p = CFG[cfg]()
+    ctx = host.TaaContext((w, h))
+    hist_ref = np.zeros((h, w, 4), np.float16)
+    hist_free = hist_ref.copy()
+    prev_depth = None
+    worst, fix_total = 0.0, 0
+    for n in range(64):
+        f = sc.frame(n)
+        ins = np_inputs(f)
+        u = configs.uniforms_for(p, f.jitter_ndc, reset_history=(n == 0))
+        hd = prev_depth if prev_depth is not None else ins["depth"]
+        ref, got, d, fix = check_tuned(oracle, u, ins, hist_ref, hist_depth=hd, ctx=ctx)
+        worst = max(worst, d)
+        fix_total += fix
+        free = run_gpu_resolve(ctx, u, ins, hist_free, hist_depth=hd)
+        hist_ref, hist_free = ref["history_out"], free["history_out"]
+        prev_depth = ins["depth"]
+    q = psnr(ref["result"][..., :3], free["result"][..., :3])
+    assert q >= PSNR_MIN, f"PSNR after 64 free-running frames: {q:.1f} dB"
+    d_free = max_abs_nan_aware(ref["result"], free["result"])
+    print(f"{cfg}: worst per-frame |d| = {worst:.3e}, free-running |d| after 64 frames = {d_free:.3e}, PSNR = {q:.1f} dB, "
+          f"fix-up pixels per frame = {fix_total / 64:.0f} of {w * h}")
+    if cfg == "config3":
+        assert 0.001 < (ref["mask"] & 1).mean() < 0.5
+
+
+@pytest.mark.parametrize("nbands", [2, 3])
+def test_row_bands_equal_whole_frame(oracle, nbands):
+    sc = SyntheticScene(W, H, pan_px=(3.0, 4.5))
+    f0, f1 = sc.frame(3), sc.frame(4)
+    ins = np_inputs(f1)
+    hist = random_history(H, W, 13)
+    u = configs.uniforms_for(configs.config3_full_chain(), f1.jitter_ndc)
+    ref, whole, _, _ = check_tuned(oracle, u, ins, hist, hist_depth=f0.depth.numpy())
+    halo = 12
+    for b in range(nbands):
+        y0, y1 = b * H // nbands, (b + 1) * H // nbands
+        a, e = max(0, y0 - halo), min(H, y1 + halo)
+        ctx = host.TaaContext((W, H), band=(y0, y1 - y0))
+        out = {k: torch.zeros(y1 - y0, W, 4, dtype=torch.float16, device="cuda") for k in ("history_out", "result")}
+        mask = torch.zeros(y1 - y0, W, dtype=torch.int32, device="cuda")
+        sl = lambda arr: (to_dev(arr[a:e]), a)
+        ctx.resolve(u, color=sl(ins["color"]), depth=sl(ins["depth"]), velocity=sl(ins["velocity"]), history_in=sl(hist),
+                    history_depth=sl(f0.depth.numpy()), history_out=(out["history_out"], y0), result=(out["result"], y0), mask=(mask, y0))
+        assert ctx.poll_status() == abi.TAA_OK
+        assert ctx.launch_count == 2
+        for k in out:  # a band runs the same per-pixel arithmetic as the whole frame
+            assert (out[k].cpu().numpy().view(np.uint16) == whole[k][y0:y1].view(np.uint16)).all(), (k, y0, y1)
+        assert (ref["mask"][y0:y1] == mask.cpu().numpy().view(np.uint32)).all()
+        ctx.close()
+
+
+def test_band_halo_overflow_is_reported():
+    sc = SyntheticScene(W, H, pan_px=(0.0, 40.0))
+    f1 = sc.frame(1)
+    ins = np_inputs(f1)
+    hist = random_history(H, W, 13)
+    u = configs.uniforms_for(configs.config2_resolve(), f1.jitter_ndc)
+    y0, y1, halo = 48, 96, 4
+    ctx = host.TaaContext((W, H), band=(y0, y1 - y0))
+    a, b = y0 - halo, y1 + halo
+    sl = lambda arr: (to_dev(arr[a:b]), a)
+    out = torch.zeros(y1 - y0, W, 4, dtype=torch.float16, device="cuda")
+    ctx.resolve(u, color=sl(ins["color"]), depth=sl(ins["depth"]), velocity=sl(ins["velocity"]), history_in=sl(hist), history_out=(out, y0))
+    assert ctx.poll_status() == abi.TAA_E_HALO_OVERFLOW
+
+
+def _gpu_frame_pair(w, h, device, n=9, **kw):
+    sc = SyntheticScene(w, h, device=device, with_aux=False, **kw)
+    return sc.frame(n - 1), sc.frame(n)
+
+
+@pytest.mark.parametrize("cfg", ["config2", "config3"])
+def test_full_size_4k_against_exact_kernel_and_oracle_rows(oracle, cfg):
+    """3840x2160 (BASELINE configs[1], [2]): tuned path vs the exact GPU kernel on the whole frame (masks identical, colour within 2^-10),
+    and vs the oracle on sampled row bands."""
+    w, h = 3840, 2160
+    dev = torch.device("cuda")
+    f0, f1 = _gpu_frame_pair(w, h, dev)
+    u = configs.uniforms_for(CFG[cfg](), f1.jitter_ndc)
+    hist = f0.color.clone()
+    hist[..., 3] = (torch.rand(h, w, device=dev) > 0.8).to(torch.float16)
+    outs = {}
+    for name, flags in (("tuned", 0), ("exact", abi.TAA_FLAG_EXACT)):
+        ctx = host.TaaContext((w, h), flags=flags)
+        o = {k: torch.zeros(h, w, 4, dtype=torch.float16, device=dev) for k in ("history_out", "result")}
+        o["mask"] = torch.zeros(h, w, dtype=torch.int32, device=dev)
+        ctx.resolve(u, color=f1.color, depth=f1.depth, velocity=f1.velocity, history_in=hist, history_depth=f0.depth, **o)
+        torch.cuda.synchronize()
+        if name == "tuned":
+            fix = ctx.fixup_pixels()
+        outs[name] = o
+        ctx.close()
+    assert torch.equal(outs["tuned"]["mask"], outs["exact"]["mask"]), \
+        f"{int((outs['tuned']['mask'] != outs['exact']['mask']).sum())} mask values differ at 4K ({fix} pixels went through the fix-up)"
+    for k in ("history_out", "result"):
+        d = float((outs["tuned"][k].float() - outs["exact"][k].float()).abs().max())
+        assert d <= TOL_ABS, f"{k}: max |d| = {d}"
+    print(f"{cfg} 4K: fix-up pixels = {fix} ({100.0 * fix / (w * h):.3f} %), rectified = {float((outs['exact']['mask'] & 2).bool().float().mean()):.3f}")
+    # oracle on three row bands of the same frame
+    ins = dict(color=f1.color.cpu().numpy(), depth=f1.depth.cpu().numpy(), velocity=f1.velocity.cpu().numpy())
+    hist_np, hd_np = hist.cpu().numpy(), f0.depth.cpu().numpy()
+    for ya in (0, 1000, h - 24):
+        ref = oracle.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist_np, history_depth=hd_np, want=("history_out", "mask"), rows=(ya, ya + 24))
+        got = outs["tuned"]["history_out"][ya:ya + 24].cpu().numpy()
+        assert max_abs_nan_aware(ref["history_out"][ya:ya + 24], got) <= TOL_ABS
+        assert (ref["mask"][ya:ya + 24] == outs["tuned"]["mask"][ya:ya + 24].cpu().numpy().view(np.uint32)).all()
+
+
+def test_16k_wide_strip(oracle):
+    """A 15360-wide strip (BASELINE configs[3] width): the sampler's coordinate rounding is 4x that of 4K."""
+    w, h = 15360, 40
+    sc = SyntheticScene(w, h, pan_px=(3.0, 0.5))
+    f0, f1 = sc.frame(4), sc.frame(5)
+    u = configs.uniforms_for(configs.config2_resolve(), f1.jitter_ndc)
+    check_tuned(oracle, u, np_inputs(f1), f0.color.numpy().copy())
