@@ -206,6 +206,11 @@ def run_single(args):
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_PX[cfg_id] * px / (ms_per_step * 1e-3) / 1e9
 
+    if args.kernel_only:  # tuning aid: device-timed kernel numbers only
+        print(json.dumps({"kernel_only": True, "config": cfg_id, "ms_per_step": round(ms_per_step, 5), "Mpixels/s": round(mpx_s, 1),
+                          "frac": round(achieved / peak, 4), "gpu_launches": int(launches), "fixup_pixels": ctx.fixup_pixels(),
+                          "variant": os.environ.get("TAA_TUNED_VARIANT")}), flush=True)
+        return
     # ---- e2e: host buffers through the invokee (taa<CF>::render path), H2D + D2H inside the timed region ----
     t = host.Taa(3, flags=flags)
     t.set_sizes_for_host_frames((W, H), (W, H))
@@ -285,6 +290,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3])
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and CPU legs (tuning aid; not a bench line)")
     ap.add_argument("--exact", action="store_true", help="TAA_FLAG_EXACT: force the exact general kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -43,10 +43,10 @@ constexpr int S_ITERS = (SW * SH + NT - 1) / NT;
 constexpr float FIXUP_BAND_4K = 4.0e-5f;
 
 // sampler footprints that depend on the column or on the row only, as byte offsets into the image
-struct ColX { int m, n; float p; };                 // colour tap: main texel, bleeding neighbour (byte offsets in a row), its weight
-struct ColY { long long m, n; float p; int pad; };  // same for rows (byte offsets of the rows in the buffer)
-struct VelX { int o0, o1; float a, u; };            // velocity tap: exact bilinear footprint and the pixel's u (taa.comp:131)
-struct VelY { long long o0, o1; float a, v; };
+struct ColX { unsigned int m, n; float p; };                 // colour tap: main texel, bleeding neighbour (byte offsets in a row), its weight
+struct ColY { unsigned int m, n; float p; };  // same for rows (byte offsets of the rows in the buffer)
+struct VelX { unsigned int o0, o1; float a, u; };            // velocity tap: exact bilinear footprint and the pixel's u (taa.comp:131)
+struct VelY { unsigned int o0, o1; float a, v; };
 
 struct __align__(16) Smem {
 	float4 S[SH][SW];
@@ -62,15 +62,16 @@ __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ __half2 h2(unsigned int v) { return *reinterpret_cast<__half2*>(&v); }
 
-// byte offset of global row gy in a (band) buffer; rows the buffer does not hold are clamped into it and reported
+// byte offset of global row gy in a (band) buffer; rows the buffer does not hold are clamped into it and reported.
+// 32-bit: tuned_supports() admits only buffers smaller than 4 GB, so that addresses are uniform base + 32-bit offset.
 template <class I>
-__device__ __forceinline__ long long row_off(const I& im, int gy, unsigned int* status) {
+__device__ __forceinline__ unsigned int row_off(const I& im, int gy, unsigned int* status) {
 	int ly = gy - im.y0;
 	if ((unsigned int)ly >= (unsigned int)im.rows) {
 		if (status) atomicOr(status, 1u);
 		ly = ly < 0 ? 0 : im.rows - 1;
 	}
-	return (long long)ly * im.pitch;
+	return (unsigned int)ly * (unsigned int)im.pitch;
 }
 
 // taa.comp:207: offset + vec2(iuv + d + 0.5) * invsize with offset = 0, through the sampler (exact coordinate arithmetic)
@@ -110,27 +111,33 @@ __device__ __forceinline__ AxisW catmull_axis(float h, float size, float inv) {
 
 struct Hist { float r, g, b, a; unsigned int abits; };
 
-// the 4x4 footprint. INTERIOR: no texel is clamped and all rows are in the buffer -> one base pointer, immediate offsets.
-template <bool REJ, bool INTERIOR>
-__device__ __forceinline__ Hist gather_history(const Img& him, const AxisW& ax, const AxisW& ay, int W, int H, unsigned int* st) {
-	Hist o = {0.f, 0.f, 0.f, 0.f, 0u};
-	const unsigned char* base = nullptr;
-	int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+// the 16 texels of the 4x4 footprint. INTERIOR: no texel is clamped and all rows are in the buffer -> one base pointer, immediate offsets.
+template <bool INTERIOR>
+__device__ __forceinline__ void load_history(const Img& him, int kx, int ky, int W, int H, unsigned int* st, uint2 (&q)[16]) {
 	if (INTERIOR) {
-		base = him.p + (long long)(ay.k - 1 - him.y0) * him.pitch + (long long)(ax.k - 1) * 8;
+		const unsigned int pitch = (unsigned int)him.pitch;
+		const unsigned int base = (unsigned int)(ky - 1 - him.y0) * pitch + (unsigned int)(kx - 1) * 8u;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const uint2* hp = reinterpret_cast<const uint2*>(him.p + (base + i * pitch));
+			q[4 * i] = __ldg(hp); q[4 * i + 1] = __ldg(hp + 1); q[4 * i + 2] = __ldg(hp + 2); q[4 * i + 3] = __ldg(hp + 3);
+		}
 	} else {
-		c0 = iclamp(ax.k - 1, 0, W - 1); c1 = iclamp(ax.k, 0, W - 1); c2 = iclamp(ax.k + 1, 0, W - 1); c3 = iclamp(ax.k + 2, 0, W - 1);
+		const int c0 = iclamp(kx - 1, 0, W - 1), c1 = iclamp(kx, 0, W - 1), c2 = iclamp(kx + 1, 0, W - 1), c3 = iclamp(kx + 2, 0, W - 1);
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const uint2* hp = reinterpret_cast<const uint2*>(him.p + (size_t)row_off(him, iclamp(ky - 1 + i, 0, H - 1), st));
+			q[4 * i] = __ldg(hp + c0); q[4 * i + 1] = __ldg(hp + c1); q[4 * i + 2] = __ldg(hp + c2); q[4 * i + 3] = __ldg(hp + c3);
+		}
 	}
+}
+
+template <bool REJ>
+__device__ __forceinline__ Hist filter_history(const uint2 (&q)[16], const AxisW& ax, const AxisW& ay) {
+	Hist o = {0.f, 0.f, 0.f, 0.f, 0u};
 #pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		uint2 q0, q1, q2, q3;
-		if (INTERIOR) {
-			const uint2* hp = reinterpret_cast<const uint2*>(base + i * him.pitch);
-			q0 = __ldg(hp); q1 = __ldg(hp + 1); q2 = __ldg(hp + 2); q3 = __ldg(hp + 3);
-		} else {
-			const uint2* hp = reinterpret_cast<const uint2*>(him.p + row_off(him, iclamp(ay.k - 1 + i, 0, H - 1), st));
-			q0 = __ldg(hp + c0); q1 = __ldg(hp + c1); q2 = __ldg(hp + c2); q3 = __ldg(hp + c3);
-		}
+		const uint2 q0 = q[4 * i], q1 = q[4 * i + 1], q2 = q[4 * i + 2], q3 = q[4 * i + 3];
 		const float2 e0 = __half22float2(h2(q0.x)), e1 = __half22float2(h2(q1.x)), e2 = __half22float2(h2(q2.x)), e3 = __half22float2(h2(q3.x));
 		const float wy = ay.w[i];
 		o.r = fmaf(wy, fmaf(ax.w[3], e3.x, fmaf(ax.w[2], e2.x, fmaf(ax.w[1], e1.x, ax.w[0] * e0.x))), o.r);
@@ -170,19 +177,19 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		ColX t;
 		int m, n;
 		colour_axis(x0 - 1 + tid, invw, W, m, n, t.p);
-		t.m = m * 8; t.n = n * 8;
+		t.m = (unsigned int)m * 8u; t.n = (unsigned int)n * 8u;
 		sm.ccol[tid] = t;
 	} else if (tid >= 64 && tid < 64 + rows_valid + 2) {
 		ColY t;
 		int m, n;
 		colour_axis(y0 - 1 + (tid - 64), invh, H, m, n, t.p);
-		t.m = row_off(A.color, m, st); t.n = row_off(A.color, n, st); t.pad = 0;
+		t.m = row_off(A.color, m, st); t.n = row_off(A.color, n, st);
 		sm.crow[tid - 64] = t;
 	} else if (tid >= 128 && tid < 128 + TW) {
 		const int x = min(x0 + (tid - 128), W - 1);
 		const float u = ((float)x + 0.5f) / fW;  // tc_to_uv, taa.comp:131
 		Lin L = lin_coord(u, W);
-		VelX t = {L.i0 * 8, L.i1 * 8, L.a, u};
+		VelX t = {(unsigned int)L.i0 * 8u, (unsigned int)L.i1 * 8u, L.a, u};
 		sm.vcol[tid - 128] = t;
 	} else if (tid >= 192 && tid < 192 + rows_valid) {
 		const int y = y0 + (tid - 192);
@@ -195,7 +202,7 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 	// bilinear footprint lies inside the 5x5 texels around the pixel; where all of them have w == +-0 the taps return w == 0 exactly.
 	if (REJ && P.mDynamicAntiGhosting) {
 		for (int r = warp; r < rows_valid + 4; r += NWARP) {
-			const uint2* vp = reinterpret_cast<const uint2*>(A.velocity.p + row_off(A.velocity, iclamp(y0 - 2 + r, 0, H - 1), st));
+			const uint2* vp = reinterpret_cast<const uint2*>(A.velocity.p + (size_t)row_off(A.velocity, iclamp(y0 - 2 + r, 0, H - 1), st));
 			const unsigned int wa = __ldg(vp + iclamp(x0 - 2 + lane, 0, W - 1)).y & 0x7fff0000u;
 			const unsigned int wb = lane < 4 ? (__ldg(vp + iclamp(x0 + 30 + lane, 0, W - 1)).y & 0x7fff0000u) : 0u;
 			const unsigned int lo = __ballot_sync(0xffffffffu, wa != 0u), hi = __ballot_sync(0xffffffffu, wb != 0u);
@@ -217,10 +224,9 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 			const int r = idx / SW, c = idx - r * SW;
 			const ColX cx = sm.ccol[c];
 			const ColY cy = sm.crow[r];
-			const unsigned char* rm = A.color.p + cy.m;
-			M[k] = __ldg(reinterpret_cast<const uint2*>(rm + cx.m));
-			NX[k] = __ldg(reinterpret_cast<const uint2*>(rm + cx.n));
-			NY[k] = __ldg(reinterpret_cast<const uint2*>(A.color.p + cy.n + cx.m));
+			M[k] = __ldg(reinterpret_cast<const uint2*>(A.color.p + (cy.m + cx.m)));
+			NX[k] = __ldg(reinterpret_cast<const uint2*>(A.color.p + (cy.m + cx.n)));
+			NY[k] = __ldg(reinterpret_cast<const uint2*>(A.color.p + (cy.n + cx.m)));
 			pxs[k] = cx.p; pys[k] = cy.p;
 		}
 #pragma unroll
@@ -253,12 +259,13 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 	const int hlo = max(0, A.history_in.y0), hhi = min(H - 1, A.history_in.y0 + A.history_in.rows - 1);
 	// output pointers of this thread's column, walking down the strip
 	const int xs = min(x, W - 1);
-	unsigned char* p_hist = A.history_out.p + (long long)(y0 + r0 - A.history_out.y0) * A.history_out.pitch + (long long)xs * 8;
-	unsigned char* p_res = A.result.p ? A.result.p + (long long)(y0 + r0 - A.result.y0) * A.result.pitch + (long long)xs * 8 : nullptr;
-	unsigned char* p_mask = A.mask.p ? A.mask.p + (long long)(y0 + r0 - A.mask.y0) * A.mask.pitch + (long long)xs * 4 : nullptr;
-	const unsigned char* p_depth = nullptr;
-	if (REJ) p_depth = A.depth.p + row_off(A.depth, y0 + r0, st) + (long long)xs * 4;
+	unsigned int o_hist = (unsigned int)(y0 + r0 - A.history_out.y0) * (unsigned int)A.history_out.pitch + (unsigned int)xs * 8u;
+	unsigned int o_res = (unsigned int)(y0 + r0 - A.result.y0) * (unsigned int)A.result.pitch + (unsigned int)xs * 8u;
+	unsigned int o_mask = (unsigned int)(y0 + r0 - A.mask.y0) * (unsigned int)A.mask.pitch + (unsigned int)xs * 4u;
+	unsigned int o_depth = 0u;
+	if (REJ) o_depth = row_off(A.depth, y0 + r0, st) + (unsigned int)xs * 4u;
 
+	const float gg = P.mVarClipGamma * P.mVarClipGamma, gg9 = gg * (1.0f / 9.0f);
 	// row sums of the first two neighbourhood rows of the strip
 	float3 s1a, s2a, s1b, s2b, cur_next;
 	{
@@ -273,11 +280,50 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		cur_next = make_float3(b.x, b.y, b.z);
 	}
 
+	// velocity footprint of the first pixel of the strip; the next one is requested while the current pixel is filtered
+	uint2 vt00, vt10, vt01, vt11;
+	{
+		const VelY vr = sm.vrow[r0];
+		vt00 = __ldg(reinterpret_cast<const uint2*>(A.velocity.p + (vr.o0 + vc.o0))); vt10 = __ldg(reinterpret_cast<const uint2*>(A.velocity.p + (vr.o0 + vc.o1)));
+		vt01 = __ldg(reinterpret_cast<const uint2*>(A.velocity.p + (vr.o1 + vc.o0))); vt11 = __ldg(reinterpret_cast<const uint2*>(A.velocity.p + (vr.o1 + vc.o1)));
+	}
+
 #pragma unroll
 	for (int rr = 0; rr < RPT; ++rr) {
 		const int rt = r0 + rr;  // tile row of this pixel
 		if (rt >= rows_valid) break;
 		const int y = y0 + rt;
+
+		// ---- getHistoryPosition (taa.comp:391-438), exact ----
+		const VelY vr = sm.vrow[rt];
+		const float v = vr.v;
+		float velx, vely, velz = 0.f;
+		bool movC = false;
+		{
+			const float2 a00 = __half22float2(h2(vt00.x)), a10 = __half22float2(h2(vt10.x)), a01 = __half22float2(h2(vt01.x)), a11 = __half22float2(h2(vt11.x));
+			velx = lerpf(lerpf(a00.x, a10.x, vc.a), lerpf(a01.x, a11.x, vc.a), vr.a);
+			vely = lerpf(lerpf(a00.y, a10.y, vc.a), lerpf(a01.y, a11.y, vc.a), vr.a);
+			if (REJ) {
+				const float2 b00 = __half22float2(h2(vt00.y)), b10 = __half22float2(h2(vt10.y)), b01 = __half22float2(h2(vt01.y)), b11 = __half22float2(h2(vt11.y));
+				velz = lerpf(lerpf(b00.x, b10.x, vc.a), lerpf(b01.x, b11.x, vc.a), vr.a);
+				const float velw = lerpf(lerpf(b00.y, b10.y, vc.a), lerpf(b01.y, b11.y, vc.a), vr.a);
+				movC = (fabsf(velx) > 1e-5f || fabsf(vely) > 1e-5f) && (fabsf(velw) >= 0.5f);
+			}
+		}
+		const float hu = u - velx, hv = v - vely;
+
+		// ---- history: request the 4x4 Catmull-Rom footprint, then do the neighbourhood statistics while it arrives ----
+		const AxisW ax = catmull_axis(hu, fW, invw), ay = catmull_axis(hv, fH, invh);
+		const bool interior = (unsigned int)(ax.k - 1) <= (unsigned int)(W - 4) && ay.k - 1 >= hlo && ay.k + 2 <= hhi;
+		uint2 q[16];
+		if (interior) load_history<true>(A.history_in, ax.k, ay.k, W, H, st, q);
+		else load_history<false>(A.history_in, ax.k, ay.k, W, H, st, q);
+		if (rr + 1 < RPT && rt + 1 < rows_valid) {
+			const VelY vn = sm.vrow[rt + 1];
+			vt00 = __ldg(reinterpret_cast<const uint2*>(A.velocity.p + (vn.o0 + vc.o0))); vt10 = __ldg(reinterpret_cast<const uint2*>(A.velocity.p + (vn.o0 + vc.o1)));
+			vt01 = __ldg(reinterpret_cast<const uint2*>(A.velocity.p + (vn.o1 + vc.o0))); vt11 = __ldg(reinterpret_cast<const uint2*>(A.velocity.p + (vn.o1 + vc.o1)));
+		}
+
 		const float3 cur = cur_next;
 		float3 s1c, s2c;
 		{
@@ -287,40 +333,15 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 			cur_next = make_float3(b.x, b.y, b.z);
 		}
 		// ---- variance box (taa.comp:266-277) ----
+		// mean = m1 / 9, extent = gamma * sqrt(max(0, m2 / 9 - mean^2)) = sqrt(max(0, (gamma^2 / 9) m2 - gamma^2 mean^2))
 		const float ninth = 1.0f / 9.0f;
 		const float3 mean = make_float3((s1a.x + s1b.x + s1c.x) * ninth, (s1a.y + s1b.y + s1c.y) * ninth, (s1a.z + s1b.z + s1c.z) * ninth);
-		const float3 msq = make_float3((s2a.x + s2b.x + s2c.x) * ninth, (s2a.y + s2b.y + s2c.y) * ninth, (s2a.z + s2b.z + s2c.z) * ninth);
-		const float g = P.mVarClipGamma;
-		const float3 ext = make_float3(g * sqrt_approx(fmaxf(0.f, fmaf(-mean.x, mean.x, msq.x))), g * sqrt_approx(fmaxf(0.f, fmaf(-mean.y, mean.y, msq.y))),
-		                               g * sqrt_approx(fmaxf(0.f, fmaf(-mean.z, mean.z, msq.z))));
+		const float3 ext = make_float3(sqrt_approx(fmaxf(0.f, fmaf(-gg * mean.x, mean.x, (s2a.x + s2b.x + s2c.x) * gg9))),
+		                               sqrt_approx(fmaxf(0.f, fmaf(-gg * mean.y, mean.y, (s2a.y + s2b.y + s2c.y) * gg9))),
+		                               sqrt_approx(fmaxf(0.f, fmaf(-gg * mean.z, mean.z, (s2a.z + s2b.z + s2c.z) * gg9))));
 		s1a = s1b; s2a = s2b; s1b = s1c; s2b = s2c;
 
-		// ---- getHistoryPosition (taa.comp:391-438), exact ----
-		const VelY vr = sm.vrow[rt];
-		const float v = vr.v;
-		float velx, vely, velz = 0.f;
-		bool movC = false;
-		{
-			const unsigned char* p0 = A.velocity.p + vr.o0;
-			const unsigned char* p1 = A.velocity.p + vr.o1;
-			const uint2 t00 = __ldg(reinterpret_cast<const uint2*>(p0 + vc.o0)), t10 = __ldg(reinterpret_cast<const uint2*>(p0 + vc.o1));
-			const uint2 t01 = __ldg(reinterpret_cast<const uint2*>(p1 + vc.o0)), t11 = __ldg(reinterpret_cast<const uint2*>(p1 + vc.o1));
-			const float2 a00 = __half22float2(h2(t00.x)), a10 = __half22float2(h2(t10.x)), a01 = __half22float2(h2(t01.x)), a11 = __half22float2(h2(t11.x));
-			velx = lerpf(lerpf(a00.x, a10.x, vc.a), lerpf(a01.x, a11.x, vc.a), vr.a);
-			vely = lerpf(lerpf(a00.y, a10.y, vc.a), lerpf(a01.y, a11.y, vc.a), vr.a);
-			if (REJ) {
-				const float2 b00 = __half22float2(h2(t00.y)), b10 = __half22float2(h2(t10.y)), b01 = __half22float2(h2(t01.y)), b11 = __half22float2(h2(t11.y));
-				velz = lerpf(lerpf(b00.x, b10.x, vc.a), lerpf(b01.x, b11.x, vc.a), vr.a);
-				const float velw = lerpf(lerpf(b00.y, b10.y, vc.a), lerpf(b01.y, b11.y, vc.a), vr.a);
-				movC = (fabsf(velx) > 1e-5f || fabsf(vely) > 1e-5f) && (fabsf(velw) >= 0.5f);
-			}
-		}
-		const float hu = u - velx, hv = v - vely;
-
-		// ---- history: 4x4 Catmull-Rom footprint with separable weights ----
-		const AxisW ax = catmull_axis(hu, fW, invw), ay = catmull_axis(hv, fH, invh);
-		const bool interior = (unsigned int)(ax.k - 1) <= (unsigned int)(W - 4) && ay.k - 1 >= hlo && ay.k + 2 <= hhi;
-		const Hist hs = interior ? gather_history<REJ, true>(A.history_in, ax, ay, W, H, st) : gather_history<REJ, false>(A.history_in, ax, ay, W, H, st);
+		const Hist hs = filter_history<REJ>(q, ax, ay);
 		float3 hist;  // maybe_rgb_to_ycocg(historyRaw.rgb), taa.comp:769
 		{
 			const float t = hs.r + hs.b, hg2 = 0.5f * hs.g;
@@ -351,8 +372,8 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 						// tap's sampler bleed reaches a texel of the 6x6 ring with alpha != 0
 						unsigned int ring = 0x7fff0000u;
 						if ((unsigned int)(ax.k - 2) <= (unsigned int)(W - 6) && ay.k - 2 >= hlo && ay.k + 3 <= hhi) {
-							const unsigned char* rb = A.history_in.p + (long long)(ay.k - 2 - A.history_in.y0) * A.history_in.pitch + (long long)(ax.k - 2) * 8 + 4;
-							const long long hp = A.history_in.pitch;
+							const unsigned int hp = (unsigned int)A.history_in.pitch;
+							const unsigned char* rb = A.history_in.p + ((unsigned int)(ay.k - 2 - A.history_in.y0) * hp + (unsigned int)(ax.k - 2) * 8u + 4u);
 							ring = 0u;
 #pragma unroll
 							for (int j = 0; j < 6; ++j) ring |= __ldg(reinterpret_cast<const unsigned int*>(rb + j * 8)) | __ldg(reinterpret_cast<const unsigned int*>(rb + 5 * hp + j * 8));
@@ -365,13 +386,13 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 				writeDynamicMask = movC ? 1.0f : 0.0f;
 			}
 			if (P.mDepthCulling) {
-				const float depth = __ldg(reinterpret_cast<const float*>(p_depth));
+				const float depth = __ldg(reinterpret_cast<const float*>(A.depth.p + o_depth));
 				const float expected = depth - velz;
 				const int tx = (int)(hu * fW), ty = (int)(hv * fH);
 				const float hd = fetch_r32f(A.history_depth, W, H, tx, ty, st);
 				if (fabsf(hd - expected) > 0.1f * (1.0f - hd)) rejected = true;
 			}
-			p_depth += A.depth.pitch;
+			o_depth += (unsigned int)A.depth.pitch;
 		}
 
 		// ---- clipAabb towards the box centre (taa.comp:323-345) ----
@@ -419,13 +440,13 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		if (xvalid) {
 			const __half2 rg = __floats2half2_rn(outr, outg);
 			const __half2 bm = __floats2half2_rn(outb, writeDynamicMask), b1 = __floats2half2_rn(outb, 1.0f);
-			*reinterpret_cast<uint2*>(p_hist) = make_uint2(*reinterpret_cast<const unsigned int*>(&rg), *reinterpret_cast<const unsigned int*>(&bm));
-			if (p_res) *reinterpret_cast<uint2*>(p_res) = make_uint2(*reinterpret_cast<const unsigned int*>(&rg), *reinterpret_cast<const unsigned int*>(&b1));
-			if (p_mask) *reinterpret_cast<unsigned int*>(p_mask) = (rejected ? 1u : 0u) | (rectified ? 2u : 0u) | (2u << 2);
+			*reinterpret_cast<uint2*>(A.history_out.p + o_hist) = make_uint2(*reinterpret_cast<const unsigned int*>(&rg), *reinterpret_cast<const unsigned int*>(&bm));
+			if (A.result.p) *reinterpret_cast<uint2*>(A.result.p + o_res) = make_uint2(*reinterpret_cast<const unsigned int*>(&rg), *reinterpret_cast<const unsigned int*>(&b1));
+			if (A.mask.p) *reinterpret_cast<unsigned int*>(A.mask.p + o_mask) = (rejected ? 1u : 0u) | (rectified ? 2u : 0u) | (2u << 2);
 		}
-		p_hist += A.history_out.pitch;
-		if (p_res) p_res += A.result.pitch;
-		if (p_mask) p_mask += A.mask.pitch;
+		o_hist += (unsigned int)A.history_out.pitch;
+		o_res += (unsigned int)A.result.pitch;
+		o_mask += (unsigned int)A.mask.pitch;
 
 		// ---- hand the undecidable pixels to the exact pass (one atomic per warp) ----
 		const unsigned int um = __ballot_sync(0xffffffffu, uncertain && xvalid && fix_list != nullptr);
@@ -447,6 +468,10 @@ bool tuned_supports(const ResolveArgs& A) {
 	if (U.splitScreen || U.mUpsampling || U.mBypassHistoryUpdate) return false;
 	if (A.in_w != A.out_w || A.in_h != A.out_h) return false;
 	if ((long long)A.out_w * A.out_h >= (1ll << 32)) return false;
+	const Img* ins[] = {&A.color, &A.depth, &A.velocity, &A.history_in};
+	const ImgW* outs[] = {&A.history_out, &A.result, &A.mask};
+	for (const Img* i : ins) if (i->p && (long long)i->rows * i->pitch >= (1ll << 32)) return false;  // 32-bit offsets in the kernel
+	for (const ImgW* o : outs) if (o->p && ((long long)o->rows * o->pitch >= (1ll << 32) || o->y0 > A.band_y0)) return false;
 	if (A.debug.p || A.segmask.p) return false;
 	if (P.mPassThrough || !P.mUseYCoCg || P.mShrinkChromaAxis || !P.mVarianceClipping || P.mColorClampingOrClipping != 2) return false;
 	if (P.mUnjitterNeighbourhood || P.mUnjitterCurrentSample || P.mToneMapLumaKaris || P.mAddNoise || P.mRayTraceAugment) return false;
