@@ -82,6 +82,13 @@ class ClockSampler:
         return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def cpu_impl(oracle_py):
+    """The CPU arm: the reference's own shader text compiled by oracle/ref_build.py when that library exists, else the restatement."""
+    if oracle_py.ref_available():
+        return "ref", "reference", "oracle/_ref/libtaa_ref.so (the reference's taa.comp compiled through oracle/glsl_shim.h)"
+    return "oracle", "port", "oracle/libtaa_oracle.so"
+
+
 def cpu_oracle_throughput(cfg_id: int, width: int, height: int, budget_s: float = 12.0):
     """Times the CPU restatement (oracle/) on a band of rows of the bench workload. Returns (Mpx/s, cores, sample text)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -96,19 +103,20 @@ def cpu_oracle_throughput(cfg_id: int, width: int, height: int, budget_s: float 
     hist = f0.color.numpy().copy()
     u = configs.uniforms_for(p, f1.jitter_ndc)
     cores = oracle_py.max_threads()
+    impl, kind, libname = cpu_impl(oracle_py)
     rows = min(height, 64)
     t0 = time.perf_counter()
-    oracle_py.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=f0.depth.numpy(), want=("history_out", "result"), rows=(height // 2, height // 2 + rows))
+    oracle_py.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=f0.depth.numpy(), want=("history_out", "result"), rows=(height // 2, height // 2 + rows), impl=impl)
     per_row = (time.perf_counter() - t0) / rows
     rows = int(max(64, min(height, budget_s / 3 / max(per_row, 1e-9))))
     y0 = (height - rows) // 2
     times = []
     for _ in range(3):
         t0 = time.perf_counter()
-        oracle_py.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=f0.depth.numpy(), want=("history_out", "result"), rows=(y0, y0 + rows))
+        oracle_py.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=f0.depth.numpy(), want=("history_out", "result"), rows=(y0, y0 + rows), impl=impl)
         times.append(time.perf_counter() - t0)
     best = min(times)
-    return rows * width / best / 1e6, cores, f"{rows} rows of one {width}x{height} frame (config {cfg_id}), best of 3, {cores} OpenMP threads, oracle/libtaa_oracle.so"
+    return rows * width / best / 1e6, cores, kind, f"{rows} rows of one {width}x{height} frame (config {cfg_id}), best of 3, {cores} OpenMP threads, {libname}"
 
 
 def run_reference(args):
@@ -127,12 +135,13 @@ def run_reference(args):
     hist = f0.color.numpy().copy()
     u = configs.uniforms_for(p, f1.jitter_ndc)
     cores = oracle_py.max_threads()
+    impl, kind, libname = cpu_impl(oracle_py)
     rows = 192  # bounded sample per step
     y0 = (2160 - rows) // 2
 
     def step():
         oracle_py.resolve(u, f1.color.numpy(), f1.depth.numpy(), f1.velocity.numpy(), hist, history_depth=f0.depth.numpy(),
-                          want=("history_out", "result"), rows=(y0, y0 + rows))
+                          want=("history_out", "result"), rows=(y0, y0 + rows), impl=impl)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -140,12 +149,12 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     mpx = args.steps * rows * 3840 / dt / 1e6
-    sample = f"each step = {rows} rows of a 3840x2160 frame (config {cfg_id}) through oracle/libtaa_oracle.so with {cores} OpenMP threads"
+    sample = f"each step = {rows} rows of a 3840x2160 frame (config {cfg_id}) through {libname} with {cores} OpenMP threads"
     line = {"impl": "reference", "metric": "resolved Mpixels/s", "value": round(mpx, 3), "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{width}x{height} TAA resolve, BASELINE configs[{1 if cfg_id == 2 else 2}]", "sample": sample},
-            "cpu_baseline": {"value": round(mpx, 3), "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": round(mpx, 3), "unit": "Mpixels/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(mpx, 3), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -261,7 +270,7 @@ def run_single(args):
     checksum = float(houts[(6 + e2e_steps - 1) % 3][::97, ::89, :3].float().mean())
     assert 0.05 < checksum < 0.95, f"implausible result mean {checksum}"
 
-    cpu_mpx, cores, sample = cpu_oracle_throughput(cfg_id, W, H)
+    cpu_mpx, cores, cpu_kind, sample = cpu_oracle_throughput(cfg_id, W, H)
     line = {
         "metric": "resolved Mpixels/s", "value": round(mpx_s, 1), "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -272,7 +281,7 @@ def run_single(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                      "peak_source": peak_src, "bytes_per_px": BYTES_PER_PX[cfg_id], "kernel": "taa_resolve"},
-        "cpu_baseline": {"value": round(cpu_mpx, 3), "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(cpu_mpx, 3), "unit": "Mpixels/s", "cores": cores, "kind": cpu_kind, "sample": sample},
         "e2e": {"value": round(e2e_mpx, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "fps": round(e2e_steps / e2e_dt, 1), "path": "taa_invokee_frame_host: pinned host G-buffer -> H2D -> render() -> D2H of the final image, 3 frames in flight",
                 "gpu_launches": int(t.launch_count - e2e_launch0)},

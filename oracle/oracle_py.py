@@ -52,6 +52,30 @@ def lib() -> C.CDLL:
     return _lib
 
 
+REF_LIB_PATH = os.path.join(_HERE, "_ref", "libtaa_ref.so")
+_ref = None
+
+
+def ref_available() -> bool:
+    return os.path.exists(REF_LIB_PATH)
+
+
+def ref_lib() -> C.CDLL:
+    """oracle/_ref/libtaa_ref.so: the reference's own shader sources compiled through oracle/glsl_shim.h (oracle/ref_build.py)."""
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_LIB_PATH)
+        P = C.POINTER
+        L.taa_ref_resolve.restype = C.c_int
+        L.taa_ref_resolve.argtypes = [P(abi.taa_resolve_images), P(abi.TaaUniforms)] + [C.c_int] * 7
+        L.taa_ref_sharpen.restype = C.c_int
+        L.taa_ref_sharpen.argtypes = [P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int, C.c_float]
+        L.taa_ref_post_process.restype = C.c_int
+        L.taa_ref_post_process.argtypes = [P(abi.taa_image), P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int, P(abi.TaaPostProcessPush)]
+        _ref = L
+    return _ref
+
+
 def _img(a):
     if a is None:
         return abi.taa_image(None, 0, 0, 0)
@@ -61,7 +85,7 @@ def _img(a):
 
 # numpy dtypes/shapes of the bindings: rgba16f -> (H, W, 4) uint16|float16, D32 -> (H, W) float32, r32ui -> (H, W) uint32|int32
 def resolve(uniforms: abi.TaaUniforms, color, depth, velocity, history_in, history_depth=None, prev_segmask=None, matid=None, prev_matid=None,
-            uvnrm=None, out_size=None, want=("history_out", "result"), rows=None, nthreads=0):
+            uvnrm=None, out_size=None, want=("history_out", "result"), rows=None, nthreads=0, impl="oracle"):
     """taa.comp on the CPU. Returns a dict of freshly allocated outputs named in `want`
     (any of history_out, result, debug, segmask, mask)."""
     in_h, in_w = depth.shape
@@ -80,10 +104,30 @@ def resolve(uniforms: abi.TaaUniforms, color, depth, velocity, history_in, histo
     for name, a in outs.items():
         setattr(im, name, _img(a))
     y0, y1 = rows if rows else (0, out_h)
-    st = lib().taa_oracle_resolve(C.byref(im), C.byref(uniforms), in_w, in_h, out_w, out_h, y0, y1, nthreads)
+    if impl == "ref":  # the reference's shader text itself; it has no `mask` output (that image is this repo's addition)
+        assert "mask" not in want
+        st = ref_lib().taa_ref_resolve(C.byref(im), C.byref(uniforms), in_w, in_h, out_w, out_h, y0, y1, nthreads)
+    else:
+        st = lib().taa_oracle_resolve(C.byref(im), C.byref(uniforms), in_w, in_h, out_w, out_h, y0, y1, nthreads)
     if st != 0:
-        raise RuntimeError(f"taa_oracle_resolve failed: {st}")
+        raise RuntimeError(f"taa resolve ({impl}) failed: {st}")
     return outs
+
+
+def ref_sharpen(src, factor):
+    h, w = src.shape[:2]
+    dst = np.zeros_like(src)
+    a, b = _img(src), _img(dst)
+    assert ref_lib().taa_ref_sharpen(C.byref(a), C.byref(b), w, h, factor) == 0
+    return dst
+
+
+def ref_post_process(src, debug, pc: abi.TaaPostProcessPush):
+    h, w = src.shape[:2]
+    dst = np.zeros_like(src)
+    a, b, d = _img(src), _img(dst), _img(debug)
+    assert ref_lib().taa_ref_post_process(C.byref(a), C.byref(d) if debug is not None else None, C.byref(b), w, h, C.byref(pc)) == 0
+    return dst
 
 
 def sharpen(src, factor, nthreads=0):
