@@ -266,7 +266,7 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
             "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": round(1e3 / ms_per_step, 1),
             "config": {"workload": f"{W}x{H} TAA resolve sharded in {world} row bands, BASELINE configs[3] (config {cfg_id} settings)",
-                       "arithmetic": "fast-filter" if args.fast else "exact", "halo_rows": halo,
+                       "arithmetic": "exact general kernel" if args.exact else "tuned kernel + exact fix-up pass", "halo_rows": halo,
                        "exchange": "NCCL send/recv of 2 x halo rows of history per neighbour per frame, overlapped with the interior resolve",
                        "l2": f"inputs larger than L2: {NSETS} frame sets rotated, history ping-pong"},
             "gpu_launches": int(launches.item()),
