@@ -222,7 +222,9 @@ enum {
 	 *        Every other settings block runs on the exact general kernel.
 	 * EXACT: always the general kernel: every fp32 operation in the order of the reference shader with IEEE
 	 *        round-to-nearest and no contraction; all outputs bit-identical to oracle/ on finite inputs. */
-	TAA_FLAG_EXACT = 1u << 0
+	TAA_FLAG_EXACT = 1u << 0,
+	/* testing aid: the tuned kernel hands EVERY pixel to its exact fix-up pass (validates that pass bit for bit) */
+	TAA_FLAG_FIXUP_ALL = 1u << 1
 };
 
 typedef struct taa_desc {

@@ -12,7 +12,7 @@ import os
 ABI_VERSION = 1
 
 TAA_OK, TAA_E_INVALID_ARG, TAA_E_UNSUPPORTED, TAA_E_CUDA, TAA_E_NCCL, TAA_E_HALO_OVERFLOW = 0, -1, -2, -3, -4, -5
-TAA_FLAG_DEFAULT, TAA_FLAG_EXACT = 0, 1
+TAA_FLAG_DEFAULT, TAA_FLAG_EXACT, TAA_FLAG_FIXUP_ALL = 0, 1, 2
 
 # shaders/shader_cpu_common.h:31-40
 TAA_RTFLAG_OUT, TAA_RTFLAG_DIS, TAA_RTFLAG_NRM, TAA_RTFLAG_DPT = 0x1, 0x2, 0x4, 0x8

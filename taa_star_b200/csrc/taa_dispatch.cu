@@ -23,7 +23,7 @@ cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, i
 		unsigned int* cnt = c->fix_count + c->fix_parity;
 		unsigned int* cnt_next = c->fix_count + (c->fix_parity ^ 1);
 		c->fix_parity ^= 1;
-		e = launch_resolve_tuned(A, c->fix_list, cnt, cnt_next, s);
+		e = launch_resolve_tuned(A, c->fix_list, cnt, cnt_next, (c->desc.flags & TAA_FLAG_FIXUP_ALL) != 0, s);
 		if (e != cudaSuccess) return e;
 		*launched = 1;
 		e = launch_resolve_fixup(A, c->fix_list, cnt, A.result.p != nullptr, c->num_sms, s);

@@ -15,7 +15,7 @@ cudaError_t launch_resolve_fixup(const ResolveArgs& args, const unsigned int* li
 // Appends the pixels whose `rectified` bit needs the exact arithmetic to fix_list / *fix_count and zeroes *fix_count_next.
 bool tuned_supports(const ResolveArgs& args);
 cudaError_t launch_resolve_tuned(const ResolveArgs& args, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next,
-                                 cudaStream_t stream);
+                                 bool fixup_all, cudaStream_t stream);
 
 // follow-on passes, one kernel each as the reference dispatches them (taa_post.cu)
 struct PostImg { Img src; Img debug; ImgW dst; int w, h; };

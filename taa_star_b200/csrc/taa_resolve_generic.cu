@@ -468,6 +468,169 @@ __global__ void __launch_bounds__(256) taa_resolve_generic_kernel(const __grid_c
 	resolve_pixel_exact<true>(A, x, y);
 }
 
+// The same arithmetic as resolve_pixel_exact — operation for operation — for the settings family of the tuned kernel
+// (tuned_supports(): YCoCg, variance box, clipAabb, Catmull-Rom, velocity for everything, no tonemap / unjitter / noise / TAAU /
+// seg-mask / debug), with the constant switches folded and the sampler coordinates of the 3x3 and Catmull-Rom tap grids
+// evaluated once per row and per column instead of once per tap. Used by the fix-up pass, where it is ~2.5x cheaper.
+struct RowPair { const uint2* r0; const uint2* r1; };
+__device__ __forceinline__ f3 lerp3(f3 p, f3 q, float w) { return mk3(lerpf(p.x, q.x, w), lerpf(p.y, q.y, w), lerpf(p.z, q.z, w)); }
+__device__ __forceinline__ f3 rgb_of(uint2 raw) {
+	float4 t = unpack_rgba16f(raw);
+	return mk3(t.x, t.y, t.z);
+}
+__device__ __forceinline__ f3 tap3(const RowPair& R, const Lin& X, float ya) {
+	return lerp3(lerp3(rgb_of(__ldg(R.r0 + X.i0)), rgb_of(__ldg(R.r0 + X.i1)), X.a), lerp3(rgb_of(__ldg(R.r1 + X.i0)), rgb_of(__ldg(R.r1 + X.i1)), X.a), ya);
+}
+__device__ __forceinline__ float4 tap4(const RowPair& R, const Lin& X, float ya) {
+	return lerp4(lerp4(unpack_rgba16f(__ldg(R.r0 + X.i0)), unpack_rgba16f(__ldg(R.r0 + X.i1)), X.a),
+	             lerp4(unpack_rgba16f(__ldg(R.r1 + X.i0)), unpack_rgba16f(__ldg(R.r1 + X.i1)), X.a), ya);
+}
+
+template <bool WRITE_SCREEN>
+__device__ __forceinline__ void resolve_pixel_exact_family(const ResolveArgs& A, const int x, const int y) {
+	unsigned int* st = A.status;
+	const TaaParameters& P = A.ubo.param[0];
+	const int W = A.out_w, H = A.out_h;  // input and output sizes are equal in this family
+	const float fW = (float)W, fH = (float)H;
+	const float u = ((float)x + 0.5f) / fW, v = ((float)y + 0.5f) / fH;
+	const int lx = (int)(u * fW), ly = (int)(v * fH);
+	const float invw = 1.0f / fW, invh = 1.0f / fH;
+
+	// ---- getColorAndAabb, variance branch (taa.comp:259-277); offset = vec2(0) is still added, as in the shader ----
+	f3 colMin, colMax, cur;
+	{
+		Lin cx[3], cy[3];
+		RowPair rows[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			cx[d] = lin_coord(0.0f + ((float)(lx + d - 1) + 0.5f) * invw, W);
+			cy[d] = lin_coord(0.0f + ((float)(ly + d - 1) + 0.5f) * invh, H);
+			rows[d].r0 = reinterpret_cast<const uint2*>(row_ptr(A.color, cy[d].i0, st));
+			rows[d].r1 = reinterpret_cast<const uint2*>(row_ptr(A.color, cy[d].i1, st));
+		}
+		const f3 cC = rgb_to_ycocg(tap3(rows[1], cx[1], cy[1].a));
+		const f3 c1 = rgb_to_ycocg(tap3(rows[0], cx[0], cy[0].a)), c2 = rgb_to_ycocg(tap3(rows[0], cx[1], cy[0].a)), c3 = rgb_to_ycocg(tap3(rows[0], cx[2], cy[0].a));
+		const f3 c4 = rgb_to_ycocg(tap3(rows[1], cx[0], cy[1].a)), c5 = rgb_to_ycocg(tap3(rows[1], cx[2], cy[1].a));
+		const f3 c6 = rgb_to_ycocg(tap3(rows[2], cx[0], cy[2].a)), c7 = rgb_to_ycocg(tap3(rows[2], cx[1], cy[2].a)), c8 = rgb_to_ycocg(tap3(rows[2], cx[2], cy[2].a));
+		const float N = 9.0f;
+		f3 m1 = cC + c1 + c2 + c3 + c4 + c5 + c6 + c7 + c8;
+		f3 m2 = cC * cC + c1 * c1 + c2 * c2 + c3 * c3 + c4 * c4 + c5 * c5 + c6 * c6 + c7 * c7 + c8 * c8;
+		f3 mean = m1 / N;
+		f3 var = max3(mk3(0.f, 0.f, 0.f), m2 / N - mean * mean);
+		f3 sigma = mk3(sqrtf(var.x), sqrtf(var.y), sqrtf(var.z));
+		colMin = mean - P.mVarClipGamma * sigma;
+		colMax = mean + P.mVarClipGamma * sigma;
+		cur = cC;  // getCurrentColor (taa.comp:215-220) repeats the centre tap with the same (zero) offset
+	}
+	const float depth = fetch_r32f(A.depth, W, H, lx, ly, st);
+
+	// ---- getHistoryPosition, velocity for everything, simple sample (taa.comp:391-438) ----
+	const float4 vel = tex_rgba16f(A.velocity, W, H, u, v, st);
+	const float hu = u - vel.x, hv = v - vel.y;
+	const float expectedHistoryDepth = depth - vel.z;
+	const float du = u - hu, dv = v - hv;
+	const float pixelSpeed = sqrtf(du * du + dv * dv);
+
+	// ---- sample_history_bicubic_catmullrom (taa.comp:441-514) ----
+	float4 historyRaw;
+	{
+		const float iw = 1.0f / fW, ih = 1.0f / fH;
+		const float ix = hu * fW, iy = hv * fH;
+		const float tcx = floorf(ix - 0.5f) + 0.5f, tcy = floorf(iy - 0.5f) + 0.5f;
+		const float fx = ix - tcx, fy = iy - tcy;
+		const float fx2 = fx * fx, fy2 = fy * fy, fx3 = fx2 * fx, fy3 = fy2 * fy;
+		const float w0x = -0.5f * fx3 + fx2 - 0.5f * fx, w0y = -0.5f * fy3 + fy2 - 0.5f * fy;
+		const float w1x = 1.5f * fx3 - 2.5f * fx2 + 1.0f, w1y = 1.5f * fy3 - 2.5f * fy2 + 1.0f;
+		const float w2x = -1.5f * fx3 + 2.0f * fx2 + 0.5f * fx, w2y = -1.5f * fy3 + 2.0f * fy2 + 0.5f * fy;
+		const float w3x = 0.5f * fx3 - 0.5f * fx2, w3y = 0.5f * fy3 - 0.5f * fy2;
+		const float wCx = w1x + w2x, wCy = w1y + w2y;
+		const Lin X0 = lin_coord((tcx - 1.0f) * iw, W), XC = lin_coord((tcx + w2x / wCx) * iw, W), X3 = lin_coord((tcx + 2.0f) * iw, W);
+		const Lin Y0 = lin_coord((tcy - 1.0f) * ih, H), YC = lin_coord((tcy + w2y / wCy) * ih, H), Y3 = lin_coord((tcy + 2.0f) * ih, H);
+		RowPair R0, RC, R3;
+		R0.r0 = reinterpret_cast<const uint2*>(row_ptr(A.history_in, Y0.i0, st)); R0.r1 = reinterpret_cast<const uint2*>(row_ptr(A.history_in, Y0.i1, st));
+		RC.r0 = reinterpret_cast<const uint2*>(row_ptr(A.history_in, YC.i0, st)); RC.r1 = reinterpret_cast<const uint2*>(row_ptr(A.history_in, YC.i1, st));
+		R3.r0 = reinterpret_cast<const uint2*>(row_ptr(A.history_in, Y3.i0, st)); R3.r1 = reinterpret_cast<const uint2*>(row_ptr(A.history_in, Y3.i1, st));
+		float4 r = tap4(R0, X0, Y0.a) * w0x * w0y;
+		r = r + tap4(R0, XC, Y0.a) * wCx * w0y;
+		r = r + tap4(R0, X3, Y0.a) * w3x * w0y;
+		r = r + tap4(RC, X0, YC.a) * w0x * wCy;
+		r = r + tap4(RC, XC, YC.a) * wCx * wCy;
+		r = r + tap4(RC, X3, YC.a) * w3x * wCy;
+		r = r + tap4(R3, X0, Y3.a) * w0x * w3y;
+		r = r + tap4(R3, XC, Y3.a) * wCx * w3y;
+		r = r + tap4(R3, X3, Y3.a) * w3x * w3y;
+		historyRaw = r;
+	}
+	f3 hist = rgb_to_ycocg(xyz(historyRaw));
+
+	float alpha = P.mAlpha;
+	bool rejected = false;
+	// ---- history rejection (taa.comp:787-823) ----
+	if (P.mRejectOutside) {
+		if (hu < 0.f || hv < 0.f || hu >= 1.f || hv >= 1.f) { alpha = P.mRejectionAlpha; rejected = true; }
+	}
+	float writeDynamicMask = 0.f;
+	if (P.mDynamicAntiGhosting) {
+		const float eps = 1e-5f;
+		auto mov = [&](float s, float t) {
+			float4 q = tex_rgba16f(A.velocity, W, H, s, t, st);
+			return (fabsf(q.x) > eps || fabsf(q.y) > eps) && (fabsf(q.w) >= 0.5f);
+		};
+		const bool movC = (fabsf(vel.x) > eps || fabsf(vel.y) > eps) && (fabsf(vel.w) >= 0.5f);  // the same sample as getHistoryPosition's
+		const bool movement = movC || mov(u + invw * -1.f, v + invh * 0.f) || mov(u + invw * 1.f, v + invh * 0.f) ||
+		                      mov(u + invw * 0.f, v + invh * -1.f) || mov(u + invw * 0.f, v + invh * 1.f);
+		if (!movement && historyRaw.w > 0.0f) rejected = true;
+		writeDynamicMask = movC ? 1.0f : 0.0f;
+	}
+	if (P.mDepthCulling) {
+		int tx = (int)(hu * fW), ty = (int)(hv * fH);
+		float hd = fetch_r32f(A.history_depth, W, H, tx, ty, st);
+		float depthEpsilon = 0.1f * (1.0f - hd);
+		if (fabsf(hd - expectedHistoryDepth) > depthEpsilon) rejected = true;
+	}
+
+	// ---- clipAabb(colMin, colMax, vec4(0,0,0,1), vec4(hist,1)) (taa.comp:323-345) ----
+	const f3 origHist = hist;
+	{
+		const float eps = 1e-7f;
+		f3 pClip = 0.5f * (colMax + colMin);
+		f3 e = 0.5f * (colMax - colMin);
+		f3 eClip = mk3(e.x + eps, e.y + eps, e.z + eps);
+		f3 vClip = hist - pClip;
+		f3 aUnit = abs3(vClip / eClip);
+		float maUnit = fmaxf(aUnit.x, fmaxf(aUnit.y, aUnit.z));
+		if (maUnit > 1.0f) hist = pClip + vClip / maUnit;
+	}
+	const f3 rdiff = hist - origHist;
+	const bool rectified = fabsf(rdiff.x) > 0.001f || fabsf(rdiff.y) > 0.001f || fabsf(rdiff.z) > 0.001f;
+
+	// ---- blending (taa.comp:848-900); luminance() is .x in YCoCg ----
+	if (rejected) {
+		alpha = P.mRejectionAlpha;
+	} else {
+		if (P.mVelBasedAlpha) alpha = fmaxf(alpha, mixf(alpha, P.mVelBasedAlphaMax, clampf(pixelSpeed * P.mVelBasedAlphaFactor, 0.f, 1.f)));
+		if (P.mLumaWeightingLottes) {
+			float lc = cur.x, lh = hist.x;
+			float diff = fabsf(lc - lh) / fmaxf(fmaxf(lc, lh), 0.2f);
+			float w = 1.0f - diff;
+			alpha = mixf(P.mMaxAlpha, P.mMinAlpha, w * w);
+		}
+		if (P.mReduceBlendNearClamp) {
+			float lmin = colMin.x, lmax = colMax.x, lh = origHist.x;
+			float distToClamp = 2.0f * fabsf(fminf(lh - lmin, lmax - lh)) / (lmax - lmin);
+			if (lmax - lmin < 0.001f) distToClamp = 1.0f;
+			alpha *= clampf(4.0f * distToClamp, 0.f, 1.f);
+		}
+	}
+	float beta = 1.0f;
+	if (A.ubo.mResetHistory) { alpha = 1.0f; beta = 1.0f; }
+	const float ab = alpha * beta;
+	const f3 aa = ycocg_to_rgb(mk3(mixf(hist.x, cur.x, ab), mixf(hist.y, cur.y, ab), mixf(hist.z, cur.z, ab)));
+	st_rgba16f(A.history_out, x, y, mk4(aa, writeDynamicMask));
+	if (WRITE_SCREEN) st_rgba16f(A.result, x, y, mk4(aa, 1.0f));
+	st_r32ui(A.mask, x, y, (rejected ? 1u : 0u) | (rectified ? 2u : 0u) | (2u << 2));
+}
+
 // Fix-up pass of the tuned kernels (taa_resolve_tuned.cu): the pixels whose `rectified` predicate
 // (taa.comp:845) the re-associated arithmetic could not decide safely are recomputed here with the
 // exact arithmetic, from the inputs alone. `list` holds pixels packed as y * out_w + x.
@@ -478,7 +641,7 @@ __global__ void __launch_bounds__(128) taa_resolve_fixup_kernel(const __grid_con
 	for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const unsigned int p = list[i];
 		const int y = (int)(p / (unsigned int)A.out_w), x = (int)(p - (unsigned int)y * (unsigned int)A.out_w);
-		resolve_pixel_exact<WRITE_SCREEN>(A, x, y);
+		resolve_pixel_exact_family<WRITE_SCREEN>(A, x, y);
 	}
 }
 

@@ -24,6 +24,7 @@
 //     to a list and recomputed by the exact arithmetic in a second, tiny launch (launch_resolve_fixup),
 //     which makes the mask bit-exact.
 #include "taa_device.cuh"
+#include <cmath>
 #include "taa_kernels.h"
 
 namespace taa {
@@ -349,7 +350,7 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		}
 
 		// ---- rejection (taa.comp:787-823), exact predicates ----
-		bool rejected = false, uncertain = false;
+		bool rejected = false, uncertain = fix_band > 3.0e38f;  // TAA_FLAG_FIXUP_ALL
 		float writeDynamicMask = 0.f;
 		if (REJ) {
 			if (P.mRejectOutside && (hu < 0.f || hv < 0.f || hu >= 1.f || hv >= 1.f)) rejected = true;
@@ -404,8 +405,10 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 			const float s = rcp_approx(ma);
 			hc = make_float3(fmaf(vcl.x, s, mean.x), fmaf(vcl.y, s, mean.y), fmaf(vcl.z, s, mean.z));
 			const float dx = fabsf(hc.x - hist.x), dy = fabsf(hc.y - hist.y), dz = fabsf(hc.z - hist.z);
-			rectified = fmaxf(dx, fmaxf(dy, dz)) > 0.001f;
-			if (fminf(fabsf(dx - 0.001f), fminf(fabsf(dy - 0.001f), fabsf(dz - 0.001f))) < fix_band) uncertain = true;
+			// any(greaterThan(abs(diff), 0.001)) == (largest component > 0.001): only the largest component can flip the decision
+			const float dmax = fmaxf(dx, fmaxf(dy, dz));
+			rectified = dmax > 0.001f;
+			if (fabsf(dmax - 0.001f) < fix_band) uncertain = true;
 		}
 
 		// ---- blend (taa.comp:848-900) ----
@@ -480,9 +483,10 @@ bool tuned_supports(const ResolveArgs& A) {
 	return true;
 }
 
-cudaError_t launch_resolve_tuned(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, cudaStream_t stream) {
+cudaError_t launch_resolve_tuned(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, bool fixup_all,
+                                 cudaStream_t stream) {
 	const TaaParameters& P = A.ubo.param[0];
-	const float band = FIXUP_BAND_4K * fmaxf(1.0f, fmaxf((float)A.out_w / 3840.0f, (float)A.out_h / 3840.0f));
+	const float band = fixup_all ? INFINITY : FIXUP_BAND_4K * fmaxf(1.0f, fmaxf((float)A.out_w / 3840.0f, (float)A.out_h / 3840.0f));
 	const bool rej = P.mDepthCulling || P.mRejectOutside || P.mDynamicAntiGhosting;
 	const bool alp = P.mVelBasedAlpha || P.mLumaWeightingLottes || P.mReduceBlendNearClamp;
 	dim3 block(TW * NWARP);

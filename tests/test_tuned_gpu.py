@@ -264,3 +264,30 @@ def test_16k_wide_strip(oracle):
     f0, f1 = sc.frame(4), sc.frame(5)
     u = configs.uniforms_for(configs.config2_resolve(), f1.jitter_ndc)
     check_tuned(oracle, u, np_inputs(f1), f0.color.numpy().copy())
+
+
+@pytest.mark.parametrize("sw", [dict(), dict(mVarClipGamma=0.75, mAlpha=0.3), dict(mRejectOutside=1, mDepthCulling=1, mDynamicAntiGhosting=1),
+                                dict(mVelBasedAlpha=1, mVelBasedAlphaFactor=40.0, mLumaWeightingLottes=1, mReduceBlendNearClamp=1), "config3"],
+                         ids=lambda s: s if isinstance(s, str) else ",".join(f"{k}={v}" for k, v in s.items()) or "config2")
+def test_fixup_pass_is_bit_exact(oracle, sw):
+    """TAA_FLAG_FIXUP_ALL sends every pixel through the fix-up pass (the family-specialised exact arithmetic): all outputs must then be
+    bit-identical to the oracle, including ragged sizes, borders, movers and non-finite motion."""
+    from common import mismatch_report
+    for (w, h, pan) in ((256, 144, (5.25, -2.5)), (67, 35, (0.0, 0.0)), (300, 70, (-17.0, 9.0))):
+        sc = SyntheticScene(w, h, pan_px=pan)
+        f0, f1 = sc.frame(2), sc.frame(3)
+        p = configs.config3_full_chain() if sw == "config3" else with_params(configs.config2_resolve(), **sw)
+        u = configs.uniforms_for(p, f1.jitter_ndc)
+        ins, hist = np_inputs(f1), random_history(h, w, 11)
+        if w == 300:
+            ins["velocity"].view(np.uint16)[12, 0:8, 0] = 0x7e00
+            ins["velocity"].view(np.uint16)[13, 8:16, 1] = 0x7c00
+            ins["velocity"][14, :, 0] = 60000.0
+        ref = oracle.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=f0.depth.numpy(), want=("history_out", "result", "mask"))
+        ctx = host.TaaContext((w, h), flags=abi.TAA_FLAG_FIXUP_ALL)
+        got = run_gpu_resolve(ctx, u, ins, hist, hist_depth=f0.depth.numpy())
+        assert ctx.launch_count == 2 and ctx.fixup_pixels() == w * h
+        for k in ("history_out", "result"):
+            r = mismatch_report(k, ref[k], got[k])
+            assert r is None, r
+        assert (ref["mask"] == got["mask"]).all()
