@@ -300,6 +300,9 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		const float v = vr.v;
 		float velx, vely, velz = 0.f;
 		bool movC = false;
+		unsigned long long near_movers = 0ull;  // any velocity.w != 0 among the 5x5 texels around the pixel
+		if (REJ && P.mDynamicAntiGhosting)
+			near_movers = ((sm.wmask[rt] | sm.wmask[rt + 1] | sm.wmask[rt + 2] | sm.wmask[rt + 3] | sm.wmask[rt + 4]) >> lane) & 0x1full;
 		{
 			const float2 a00 = __half22float2(h2(vt00.x)), a10 = __half22float2(h2(vt10.x)), a01 = __half22float2(h2(vt01.x)), a11 = __half22float2(h2(vt11.x));
 			velx = lerpf(lerpf(a00.x, a10.x, vc.a), lerpf(a01.x, a11.x, vc.a), vr.a);
@@ -307,8 +310,10 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 			if (REJ) {
 				const float2 b00 = __half22float2(h2(vt00.y)), b10 = __half22float2(h2(vt10.y)), b01 = __half22float2(h2(vt01.y)), b11 = __half22float2(h2(vt11.y));
 				velz = lerpf(lerpf(b00.x, b10.x, vc.a), lerpf(b01.x, b11.x, vc.a), vr.a);
-				const float velw = lerpf(lerpf(b00.y, b10.y, vc.a), lerpf(b01.y, b11.y, vc.a), vr.a);
-				movC = (fabsf(velx) > 1e-5f || fabsf(vely) > 1e-5f) && (fabsf(velw) >= 0.5f);
+				if (near_movers) {  // otherwise all four texels carry w == +-0 and the sample's w is exactly 0
+					const float velw = lerpf(lerpf(b00.y, b10.y, vc.a), lerpf(b01.y, b11.y, vc.a), vr.a);
+					movC = (fabsf(velx) > 1e-5f || fabsf(vely) > 1e-5f) && (fabsf(velw) >= 0.5f);
+				}
 			}
 		}
 		const float hu = u - velx, hv = v - vely;
@@ -360,7 +365,6 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 					return (fabsf(q.x) > 1e-5f || fabsf(q.y) > 1e-5f) && (fabsf(q.w) >= 0.5f);
 				};
 				bool movement = movC;
-				const unsigned long long near_movers = ((sm.wmask[rt] | sm.wmask[rt + 1] | sm.wmask[rt + 2] | sm.wmask[rt + 3] | sm.wmask[rt + 4]) >> lane) & 0x1full;
 				if (!movement && near_movers) movement = mov(u + invw * -1.f, v + invh * 0.f) || mov(u + invw * 1.f, v + invh * 0.f) ||
 				                                         mov(u + invw * 0.f, v + invh * -1.f) || mov(u + invw * 0.f, v + invh * 1.f);
 				if (!movement) {
