@@ -133,29 +133,25 @@ __device__ __forceinline__ void load_history(const Img& him, int kx, int ky, int
 	}
 }
 
+// one history row of the footprint filtered horizontally (4 texels, weights of the x axis)
+struct HRow { float r, g, b, a; unsigned int abits; };
 template <bool REJ>
-__device__ __forceinline__ Hist filter_history(const uint2 (&q)[16], const AxisW& ax, const AxisW& ay) {
-	Hist o = {0.f, 0.f, 0.f, 0.f, 0u};
-#pragma unroll
-	for (int i = 0; i < 4; ++i) {
-		const uint2 q0 = q[4 * i], q1 = q[4 * i + 1], q2 = q[4 * i + 2], q3 = q[4 * i + 3];
-		const float2 e0 = __half22float2(h2(q0.x)), e1 = __half22float2(h2(q1.x)), e2 = __half22float2(h2(q2.x)), e3 = __half22float2(h2(q3.x));
-		const float wy = ay.w[i];
-		o.r = fmaf(wy, fmaf(ax.w[3], e3.x, fmaf(ax.w[2], e2.x, fmaf(ax.w[1], e1.x, ax.w[0] * e0.x))), o.r);
-		o.g = fmaf(wy, fmaf(ax.w[3], e3.y, fmaf(ax.w[2], e2.y, fmaf(ax.w[1], e1.y, ax.w[0] * e0.y))), o.g);
-		if (REJ) {
-			const float2 g0 = __half22float2(h2(q0.y)), g1 = __half22float2(h2(q1.y)), g2 = __half22float2(h2(q2.y)), g3 = __half22float2(h2(q3.y));
-			o.b = fmaf(wy, fmaf(ax.w[3], g3.x, fmaf(ax.w[2], g2.x, fmaf(ax.w[1], g1.x, ax.w[0] * g0.x))), o.b);
-			o.a = fmaf(wy, fmaf(ax.w[3], g3.y, fmaf(ax.w[2], g2.y, fmaf(ax.w[1], g1.y, ax.w[0] * g0.y))), o.a);
-			o.abits |= (q0.y | q1.y) | (q2.y | q3.y);
-		} else {
-			const float g0 = __low2float(h2(q0.y)), g1 = __low2float(h2(q1.y)), g2 = __low2float(h2(q2.y)), g3 = __low2float(h2(q3.y));
-			o.b = fmaf(wy, fmaf(ax.w[3], g3, fmaf(ax.w[2], g2, fmaf(ax.w[1], g1, ax.w[0] * g0))), o.b);
-		}
+__device__ __forceinline__ HRow hfilter(const uint2 q0, const uint2 q1, const uint2 q2, const uint2 q3, const float (&w)[4]) {
+	HRow o = {0.f, 0.f, 0.f, 0.f, 0u};
+	const float2 e0 = __half22float2(h2(q0.x)), e1 = __half22float2(h2(q1.x)), e2 = __half22float2(h2(q2.x)), e3 = __half22float2(h2(q3.x));
+	o.r = fmaf(w[3], e3.x, fmaf(w[2], e2.x, fmaf(w[1], e1.x, w[0] * e0.x)));
+	o.g = fmaf(w[3], e3.y, fmaf(w[2], e2.y, fmaf(w[1], e1.y, w[0] * e0.y)));
+	if (REJ) {
+		const float2 g0 = __half22float2(h2(q0.y)), g1 = __half22float2(h2(q1.y)), g2 = __half22float2(h2(q2.y)), g3 = __half22float2(h2(q3.y));
+		o.b = fmaf(w[3], g3.x, fmaf(w[2], g2.x, fmaf(w[1], g1.x, w[0] * g0.x)));
+		o.a = fmaf(w[3], g3.y, fmaf(w[2], g2.y, fmaf(w[1], g1.y, w[0] * g0.y)));
+		o.abits = (q0.y | q1.y) | (q2.y | q3.y);
+	} else {
+		const float g0 = __low2float(h2(q0.y)), g1 = __low2float(h2(q1.y)), g2 = __low2float(h2(q2.y)), g3 = __low2float(h2(q3.y));
+		o.b = fmaf(w[3], g3, fmaf(w[2], g2, fmaf(w[1], g1, w[0] * g0)));
 	}
 	return o;
 }
-
 template <bool REJ, bool ALPHA>
 __global__ void __launch_bounds__(NT, 3)
 taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
@@ -281,6 +277,17 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		cur_next = make_float3(b.x, b.y, b.z);
 	}
 
+	// Horizontally filtered history rows are shared down the strip: with the same history u (same column, same velocity.x) the
+	// x weights are identical, and consecutive pixels' footprints overlap in 3 of their 4 rows. hr0..hr3 hold the filtered rows
+	// sh_K .. sh_K + 3 of the previous pixel; if this pixel's footprint starts exactly one row further down, only one row is new.
+	bool sh_valid = false;
+	float sh_hu = 0.f;
+	int sh_K = 0;
+	AxisW axs;
+	axs.k = 0; axs.w[0] = axs.w[1] = axs.w[2] = axs.w[3] = 0.f;
+	HRow hr0 = {0.f, 0.f, 0.f, 0.f, 0u}, hr1 = hr0, hr2 = hr0, hr3 = hr0;
+	const unsigned int hpitch = (unsigned int)A.history_in.pitch;
+
 	// velocity footprint of the first pixel of the strip; the next one is requested while the current pixel is filtered
 	uint2 vt00, vt10, vt01, vt11;
 	{
@@ -319,11 +326,28 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		const float hu = u - velx, hv = v - vely;
 
 		// ---- history: request the 4x4 Catmull-Rom footprint, then do the neighbourhood statistics while it arrives ----
-		const AxisW ax = catmull_axis(hu, fW, invw), ay = catmull_axis(hv, fH, invh);
-		const bool interior = (unsigned int)(ax.k - 1) <= (unsigned int)(W - 4) && ay.k - 1 >= hlo && ay.k + 2 <= hhi;
-		uint2 q[16];
-		if (interior) load_history<true>(A.history_in, ax.k, ay.k, W, H, st, q);
-		else load_history<false>(A.history_in, ax.k, ay.k, W, H, st, q);
+		const AxisW ay = catmull_axis(hv, fH, invh);
+		const bool shared = sh_valid && hu == sh_hu && ay.k - 1 == sh_K + 1 && sh_K + 4 <= hhi;
+		uint2 q0, q1, q2, q3;
+		if (shared) {  // one new row, sh_K + 4: requested now, filtered after the neighbourhood statistics
+			const uint2* hp = reinterpret_cast<const uint2*>(A.history_in.p + ((unsigned int)(sh_K + 4 - A.history_in.y0) * hpitch + (unsigned int)(axs.k - 1) * 8u));
+			q0 = __ldg(hp); q1 = __ldg(hp + 1); q2 = __ldg(hp + 2); q3 = __ldg(hp + 3);
+		} else {  // (re)start the window with this pixel's four rows
+			axs = catmull_axis(hu, fW, invw);
+			const bool interior = (unsigned int)(axs.k - 1) <= (unsigned int)(W - 4) && ay.k - 1 >= hlo && ay.k + 2 <= hhi;
+			uint2 q[16];
+			if (interior) load_history<true>(A.history_in, axs.k, ay.k, W, H, st, q);
+			else load_history<false>(A.history_in, axs.k, ay.k, W, H, st, q);
+			hr0 = hfilter<REJ>(q[0], q[1], q[2], q[3], axs.w);
+			hr1 = hfilter<REJ>(q[4], q[5], q[6], q[7], axs.w);
+			hr2 = hfilter<REJ>(q[8], q[9], q[10], q[11], axs.w);
+			hr3 = hfilter<REJ>(q[12], q[13], q[14], q[15], axs.w);
+			sh_K = ay.k - 1;
+			sh_hu = hu;
+			sh_valid = interior;
+			q0 = q1 = q2 = q3 = make_uint2(0u, 0u);
+		}
+		const AxisW& ax = axs;
 		if (rr + 1 < RPT && rt + 1 < rows_valid) {
 			const VelY vn = sm.vrow[rt + 1];
 			vt00 = __ldg(reinterpret_cast<const uint2*>(A.velocity.p + (vn.o0 + vc.o0))); vt10 = __ldg(reinterpret_cast<const uint2*>(A.velocity.p + (vn.o0 + vc.o1)));
@@ -347,7 +371,20 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		                               sqrt_approx(fmaxf(0.f, fmaf(-gg * mean.z, mean.z, (s2a.z + s2b.z + s2c.z) * gg9))));
 		s1a = s1b; s2a = s2b; s1b = s1c; s2b = s2c;
 
-		const Hist hs = filter_history<REJ>(q, ax, ay);
+		if (shared) {
+			hr0 = hr1; hr1 = hr2; hr2 = hr3;
+			hr3 = hfilter<REJ>(q0, q1, q2, q3, axs.w);
+			sh_K += 1;
+		}
+		Hist hs;
+		{
+			const HRow &a0 = hr0, &a1 = hr1, &a2 = hr2, &a3 = hr3;
+			hs.r = fmaf(ay.w[3], a3.r, fmaf(ay.w[2], a2.r, fmaf(ay.w[1], a1.r, ay.w[0] * a0.r)));
+			hs.g = fmaf(ay.w[3], a3.g, fmaf(ay.w[2], a2.g, fmaf(ay.w[1], a1.g, ay.w[0] * a0.g)));
+			hs.b = fmaf(ay.w[3], a3.b, fmaf(ay.w[2], a2.b, fmaf(ay.w[1], a1.b, ay.w[0] * a0.b)));
+			hs.a = REJ ? fmaf(ay.w[3], a3.a, fmaf(ay.w[2], a2.a, fmaf(ay.w[1], a1.a, ay.w[0] * a0.a))) : 0.f;
+			hs.abits = REJ ? ((a0.abits | a1.abits) | (a2.abits | a3.abits)) : 0u;
+		}
 		float3 hist;  // maybe_rgb_to_ycocg(historyRaw.rgb), taa.comp:769
 		{
 			const float t = hs.r + hs.b, hg2 = 0.5f * hs.g;
