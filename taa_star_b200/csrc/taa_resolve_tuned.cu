@@ -37,7 +37,7 @@ constexpr int RPT = 4;           // rows per thread
 constexpr int TH = NWARP * RPT;  // tile height
 constexpr int SW = TW + 2, SH = TH + 2;
 constexpr int NT = TW * NWARP;
-constexpr int S_ITERS = (SW * SH + NT - 1) / NT;
+constexpr int S_CHUNK = 5;        // sampled-colour texels per thread whose loads are in flight together (phase 1)
 // |tuned - exact| of the clip distance is dominated by the two outer Catmull-Rom taps, whose sampler bleed (<= 0.074 * eps * texel
 // contrast, eps <= ~6e-4 texel at x ~ 3840) the 4x4 footprint cannot hold: <= ~2e-5 on full-contrast edges at 4K. The band is twice
 // that and grows with the frame size like eps does.
@@ -170,30 +170,34 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 	if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && fix_count_next) *fix_count_next = 0u;  // the counter the next frame appends to
 
 	// ---- phase 0: coordinate tables ----------------------------------------------------------------
-	if (tid < SW) {
-		ColX t;
-		int m, n;
-		colour_axis(x0 - 1 + tid, invw, W, m, n, t.p);
-		t.m = (unsigned int)m * 8u; t.n = (unsigned int)n * 8u;
-		sm.ccol[tid] = t;
-	} else if (tid >= 64 && tid < 64 + rows_valid + 2) {
-		ColY t;
-		int m, n;
-		colour_axis(y0 - 1 + (tid - 64), invh, H, m, n, t.p);
-		t.m = row_off(A.color, m, st); t.n = row_off(A.color, n, st);
-		sm.crow[tid - 64] = t;
-	} else if (tid >= 128 && tid < 128 + TW) {
-		const int x = min(x0 + (tid - 128), W - 1);
-		const float u = ((float)x + 0.5f) / fW;  // tc_to_uv, taa.comp:131
-		Lin L = lin_coord(u, W);
-		VelX t = {(unsigned int)L.i0 * 8u, (unsigned int)L.i1 * 8u, L.a, u};
-		sm.vcol[tid - 128] = t;
-	} else if (tid >= 192 && tid < 192 + rows_valid) {
-		const int y = y0 + (tid - 192);
-		const float v = ((float)y + 0.5f) / fH;
-		Lin L = lin_coord(v, H);
-		VelY t = {row_off(A.velocity, L.i0, st), row_off(A.velocity, L.i1, st), L.a, v};
-		sm.vrow[tid - 192] = t;
+	static_assert(SW + SH + TW + TH <= NT, "one thread per table entry");
+	{
+		int i = tid;
+		if (i < SW) {
+			ColX t;
+			int m, n;
+			colour_axis(x0 - 1 + i, invw, W, m, n, t.p);
+			t.m = (unsigned int)m * 8u; t.n = (unsigned int)n * 8u;
+			sm.ccol[i] = t;
+		} else if ((i -= SW) < rows_valid + 2) {
+			ColY t;
+			int m, n;
+			colour_axis(y0 - 1 + i, invh, H, m, n, t.p);
+			t.m = row_off(A.color, m, st); t.n = row_off(A.color, n, st);
+			sm.crow[i] = t;
+		} else if ((i -= SH) >= 0 && i < TW) {
+			const int x = min(x0 + i, W - 1);
+			const float u = ((float)x + 0.5f) / fW;  // tc_to_uv, taa.comp:131
+			Lin L = lin_coord(u, W);
+			VelX t = {(unsigned int)L.i0 * 8u, (unsigned int)L.i1 * 8u, L.a, u};
+			sm.vcol[i] = t;
+		} else if ((i -= TW) >= 0 && i < rows_valid) {
+			const int y = y0 + i;
+			const float v = ((float)y + 0.5f) / fH;
+			Lin L = lin_coord(v, H);
+			VelY t = {row_off(A.velocity, L.i0, st), row_off(A.velocity, L.i1, st), L.a, v};
+			sm.vrow[i] = t;
+		}
 	}
 	// Movers (velocity.w != 0, fwd_geometry.frag:289-295) are what the 5-tap anti-ghosting test looks for (taa.comp:796-811). Every tap's
 	// bilinear footprint lies inside the 5x5 texels around the pixel; where all of them have w == +-0 the taps return w == 0 exactly.
@@ -213,32 +217,34 @@ taa_resolve_tuned_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 	// evaluated in packed fp16 (their own rounding error is below 1e-7); the px*py cross term (< 1e-6) is dropped.
 	{
 		const int n_s = (rows_valid + 2) * SW;
-		uint2 M[S_ITERS], NX[S_ITERS], NY[S_ITERS];
-		float pxs[S_ITERS], pys[S_ITERS];
+		for (int base = 0; base < n_s; base += S_CHUNK * NT) {  // loads of a chunk are all in flight before the first is used
+			uint2 M[S_CHUNK], NX[S_CHUNK], NY[S_CHUNK];
+			float pxs[S_CHUNK], pys[S_CHUNK];
 #pragma unroll
-		for (int k = 0; k < S_ITERS; ++k) {
-			const int idx = min(tid + k * NT, n_s - 1);
-			const int r = idx / SW, c = idx - r * SW;
-			const ColX cx = sm.ccol[c];
-			const ColY cy = sm.crow[r];
-			M[k] = __ldg(reinterpret_cast<const uint2*>(A.color.p + (cy.m + cx.m)));
-			NX[k] = __ldg(reinterpret_cast<const uint2*>(A.color.p + (cy.m + cx.n)));
-			NY[k] = __ldg(reinterpret_cast<const uint2*>(A.color.p + (cy.n + cx.m)));
-			pxs[k] = cx.p; pys[k] = cy.p;
-		}
-#pragma unroll
-		for (int k = 0; k < S_ITERS; ++k) {
-			const int idx = tid + k * NT;
-			if (idx < n_s) {
+			for (int k = 0; k < S_CHUNK; ++k) {
+				const int idx = min(base + tid + k * NT, n_s - 1);
 				const int r = idx / SW, c = idx - r * SW;
-				const __half2 px = __float2half2_rn(pxs[k]), py = __float2half2_rn(pys[k]);
-				const __half2 m01 = h2(M[k].x), m23 = h2(M[k].y);
-				const __half2 c01 = __hfma2(px, __hsub2(h2(NX[k].x), m01), __hmul2(py, __hsub2(h2(NY[k].x), m01)));
-				const __half2 c23 = __hfma2(px, __hsub2(h2(NX[k].y), m23), __hmul2(py, __hsub2(h2(NY[k].y), m23)));
-				const float2 a01 = __half22float2(m01), b01 = __half22float2(c01);
-				const float cr = a01.x + b01.x, cg = a01.y + b01.y, cb = __low2float(m23) + __low2float(c23);
-				const float t = cr + cb, hg = 0.5f * cg;
-				sm.S[r][c] = make_float4(fmaf(0.25f, t, hg), 0.5f * (cr - cb), fmaf(-0.25f, t, hg), 0.0f);
+				const ColX cx = sm.ccol[c];
+				const ColY cy = sm.crow[r];
+				M[k] = __ldg(reinterpret_cast<const uint2*>(A.color.p + (cy.m + cx.m)));
+				NX[k] = __ldg(reinterpret_cast<const uint2*>(A.color.p + (cy.m + cx.n)));
+				NY[k] = __ldg(reinterpret_cast<const uint2*>(A.color.p + (cy.n + cx.m)));
+				pxs[k] = cx.p; pys[k] = cy.p;
+			}
+#pragma unroll
+			for (int k = 0; k < S_CHUNK; ++k) {
+				const int idx = base + tid + k * NT;
+				if (idx < n_s) {
+					const int r = idx / SW, c = idx - r * SW;
+					const __half2 px = __float2half2_rn(pxs[k]), py = __float2half2_rn(pys[k]);
+					const __half2 m01 = h2(M[k].x), m23 = h2(M[k].y);
+					const __half2 c01 = __hfma2(px, __hsub2(h2(NX[k].x), m01), __hmul2(py, __hsub2(h2(NY[k].x), m01)));
+					const __half2 c23 = __hfma2(px, __hsub2(h2(NX[k].y), m23), __hmul2(py, __hsub2(h2(NY[k].y), m23)));
+					const float2 a01 = __half22float2(m01), b01 = __half22float2(c01);
+					const float cr = a01.x + b01.x, cg = a01.y + b01.y, cb = __low2float(m23) + __low2float(c23);
+					const float t = cr + cb, hg = 0.5f * cg;
+					sm.S[r][c] = make_float4(fmaf(0.25f, t, hg), 0.5f * (cr - cb), fmaf(-0.25f, t, hg), 0.0f);
+				}
 			}
 		}
 	}
