@@ -29,6 +29,15 @@ BYTES_PER_PX = {2: 44, 3: 48}  # colour 8 + depth 4 + velocity 8
 FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md
 
 
+def ncu_traffic(cfg_id: int):
+    """DRAM bytes per step of the resolve launches, from the committed `ncu --set full` capture (profiles/traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[f"config{cfg_id}"]
+        return float(t["dram_bytes_per_step"]), t["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -271,6 +280,7 @@ def run_single(args):
     assert 0.05 < checksum < 0.95, f"implausible result mean {checksum}"
 
     cpu_mpx, cores, cpu_kind, sample = cpu_oracle_throughput(cfg_id, W, H)
+    traffic, traffic_src = ncu_traffic(cfg_id) if (not args.exact and (W, H) == (3840, 2160)) else (None, None)
     line = {
         "metric": "resolved Mpixels/s", "value": round(mpx_s, 1), "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -279,8 +289,10 @@ def run_single(args):
                    "l2": f"inputs larger than L2: {NSETS} frame sets rotated ({NSETS} x {px * 20 / 1e6:.0f} MB), history ping-pong",
                    "outputs": "history_out + result"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
-                     "peak_source": peak_src, "bytes_per_px": BYTES_PER_PX[cfg_id], "kernel": "taa_resolve"},
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                     "traffic_source": traffic_src, "algorithmic_bytes": BYTES_PER_PX[cfg_id] * px,
+                     "peak_source": peak_src, "bytes_per_px": BYTES_PER_PX[cfg_id],
+                     "kernel": "taa_resolve_tuned_kernel + taa_resolve_fixup_kernel (one step)" if not args.exact else "taa_resolve_generic_kernel"},
         "cpu_baseline": {"value": round(cpu_mpx, 3), "unit": "Mpixels/s", "cores": cores, "kind": cpu_kind, "sample": sample},
         "e2e": {"value": round(e2e_mpx, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "fps": round(e2e_steps / e2e_dt, 1), "path": "taa_invokee_frame_host: pinned host G-buffer -> H2D -> render() -> D2H of the final image, 3 frames in flight",

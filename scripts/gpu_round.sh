@@ -11,7 +11,7 @@ echo "== bench"; timeout 600 python bench.py --steps 100 --warmup 5 2>&1 | tail 
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 5 --warmup 3 2>&1 | tail -3
 } > gpurun_out/round.log 2>&1
 if [ "${NCU:-1}" = "1" ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 10 --warmup 3 > gpurun_out/ncu_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:taa_resolve -s 4 -c 2 -f -o gpurun_out/prof_resolve python bench.py --steps 6 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:taa_ -c 40 --csv --log-file gpurun_out/launches.csv python bench.py --steps 10 --warmup 3 > gpurun_out/ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:taa_resolve -s 8 -c 2 -f -o gpurun_out/prof_resolve python bench.py --kernel-only --steps 8 --warmup 4 > gpurun_out/ncu_full.log 2>&1
 fi
 tail -60 gpurun_out/round.log
