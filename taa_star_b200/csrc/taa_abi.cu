@@ -294,6 +294,16 @@ int taa_frame(taa_ctx* c, const taa_resolve_images* images, const TaaUniforms* u
 		}
 		return TAA_OK;
 	}
+	if (sharpen && post) {  // [sharpen | CAS] evaluated inside the post-process pass: one launch, no intermediate image
+		if ((chain->pp.debugL_show || chain->pp.debugR_show) && !images->debug.data) { set_error(c, "post_process: debug image required when debug*_show is set"); return TAA_E_INVALID_ARG; }
+		PostImg io;
+		r = make_post(c, &last, images->debug.data ? &images->debug : nullptr, final_img, io);
+		if (r != TAA_OK) return r;
+		cudaError_t e = launch_sharpen_post(io, chain->sharpener, chain->sharpen.sharpeningFactor, chain->cas, chain->pp, (cudaStream_t)stream);
+		if (e != cudaSuccess) return cuda_fail(c, e, "sharpen + post_process launch");
+		c->launches++;
+		return TAA_OK;
+	}
 	if (sharpen) {
 		taa_image dst;
 		if (post) {

@@ -22,5 +22,7 @@ struct PostImg { Img src; Img debug; ImgW dst; int w, h; };
 cudaError_t launch_sharpen(const PostImg& io, float sharpeningFactor, cudaStream_t stream);           // sharpen.comp
 cudaError_t launch_cas(const PostImg& io, const TaaCasPush& pc, cudaStream_t stream);                 // sharpen_cas.comp
 cudaError_t launch_post_process(const PostImg& io, const TaaPostProcessPush& pc, cudaStream_t stream); // post_process.comp
+// [sharpen.comp | sharpen_cas.comp] -> post_process.comp in one pass: no intermediate image
+cudaError_t launch_sharpen_post(const PostImg& io, int sharpener, float sharpeningFactor, const TaaCasPush& cas, const TaaPostProcessPush& pc, cudaStream_t stream);
 
 }  // namespace taa

@@ -11,10 +11,8 @@ namespace {
 
 __device__ __forceinline__ f3 rgb_at(const Img& im, int w, int h, int x, int y) { return xyz(fetch_rgba16f(im, w, h, x, y, nullptr)); }
 
-// sharpen.comp:23-38
-__global__ void __launch_bounds__(256) sharpen_kernel(const __grid_constant__ PostImg io, float factor) {
-	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-	if (x >= io.w || y >= io.h) return;
+// sharpen.comp:23-38 at one pixel
+__device__ __forceinline__ float4 sharpen_at(const PostImg& io, int x, int y, float factor) {
 	f3 L = rgb_at(io.src, io.w, io.h, iclamp(x - 1, 0, io.w), iclamp(y, 0, io.h));
 	f3 R = rgb_at(io.src, io.w, io.h, iclamp(x + 1, 0, io.w), iclamp(y, 0, io.h));
 	f3 T = rgb_at(io.src, io.w, io.h, iclamp(x, 0, io.w), iclamp(y - 1, 0, io.h));
@@ -22,7 +20,12 @@ __global__ void __launch_bounds__(256) sharpen_kernel(const __grid_constant__ Po
 	f3 C = rgb_at(io.src, io.w, io.h, x, y);
 	f3 val = C + ((((4.0f * C - L) - R) - T) - B) * factor;
 	val = min3(max3(val, mk3(0.f, 0.f, 0.f)), mk3(1.f, 1.f, 1.f));
-	st_rgba16f(io.dst, x, y, mk4(val, 1.f));
+	return mk4(val, 1.f);
+}
+__global__ void __launch_bounds__(256) sharpen_kernel(const __grid_constant__ PostImg io, float factor) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= io.w || y >= io.h) return;
+	st_rgba16f(io.dst, x, y, sharpen_at(io, x, y, factor));
 }
 
 // ffx_a.h:1455-1457
@@ -32,10 +35,8 @@ __device__ __forceinline__ float prx_med_rcp(float a) { float b = __uint_as_floa
 __device__ __forceinline__ float min3f(float x, float y, float z) { return fminf(x, fminf(y, z)); }
 __device__ __forceinline__ float max3f(float x, float y, float z) { return fmaxf(x, fmaxf(y, z)); }
 
-// sharpen_cas.comp:30-53 + CasFilter(noScaling), ffx_cas.h:408-537. Only the green weight survives (ffx_cas.h:514-522).
-__global__ void __launch_bounds__(256) cas_kernel(const __grid_constant__ PostImg io, float peak) {
-	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-	if (x >= io.w || y >= io.h) return;
+// sharpen_cas.comp:30-53 + CasFilter(noScaling), ffx_cas.h:408-537, at one pixel. Only the green weight survives (ffx_cas.h:514-522).
+__device__ __forceinline__ float4 cas_at(const PostImg& io, int x, int y, float peak) {
 	f3 b = rgb_at(io.src, io.w, io.h, x, y - 1);
 	f3 d = rgb_at(io.src, io.w, io.h, x - 1, y);
 	f3 e = rgb_at(io.src, io.w, io.h, x, y);
@@ -50,11 +51,26 @@ __global__ void __launch_bounds__(256) cas_kernel(const __grid_constant__ PostIm
 	float pr = clampf((b.x * wG + d.x * wG + f.x * wG + h.x * wG + e.x) * rcpWeight, 0.f, 1.f);
 	float pg = clampf((b.y * wG + d.y * wG + f.y * wG + h.y * wG + e.y) * rcpWeight, 0.f, 1.f);
 	float pb = clampf((b.z * wG + d.z * wG + f.z * wG + h.z * wG + e.z) * rcpWeight, 0.f, 1.f);
-	st_rgba16f(io.dst, x, y, make_float4(pr, pg, pb, 1.0f));  // alpha is undefined in the reference (sharpen_cas.comp:38)
+	return make_float4(pr, pg, pb, 1.0f);  // alpha is undefined in the reference (sharpen_cas.comp:38)
+}
+__global__ void __launch_bounds__(256) cas_kernel(const __grid_constant__ PostImg io, float peak) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= io.w || y >= io.h) return;
+	st_rgba16f(io.dst, x, y, cas_at(io, x, y, peak));
 }
 
-// post_process.comp:29-88
-__global__ void __launch_bounds__(256) post_process_kernel(const __grid_constant__ PostImg io, const __grid_constant__ TaaPostProcessPush pc) {
+// The sharpener's value at (x, y) as the next pass would read it back from the rgba16f image it was stored to.
+template <int SHARPENER>
+__device__ __forceinline__ float4 stage_at(const PostImg& io, int w, int h, int x, int y, float k) {
+	if (SHARPENER == 0) return fetch_rgba16f(io.src, w, h, x, y, nullptr);
+	if (x < 0 || y < 0 || x >= w || y >= h) return make_float4(0.f, 0.f, 0.f, 0.f);
+	return unpack_rgba16f(pack_rgba16f(SHARPENER == 1 ? sharpen_at(io, x, y, k) : cas_at(io, x, y, k)));
+}
+
+// post_process.comp:29-88. SHARPENER != 0: the sharpening pass (sharpen.comp | sharpen_cas.comp) is evaluated on the fly at the pixel
+// post-process would fetch, instead of being written to and read back from an intermediate image (taa.hpp:1111-1159 does that).
+template <int SHARPENER>
+__global__ void __launch_bounds__(256) post_process_kernel(const __grid_constant__ PostImg io, const __grid_constant__ TaaPostProcessPush pc, const float k) {
 	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
 	if (x >= io.w || y >= io.h) return;
 	int fx = x, fy = y;
@@ -87,7 +103,7 @@ __global__ void __launch_bounds__(256) post_process_kernel(const __grid_constant
 		val = make_float4(dbg.x, dbg.y, dbg.z, 1.f);
 		if (maskA > 0.f) { val.x += dbg.w; val.z += dbg.w; }
 	} else {
-		val = fetch_rgba16f(io.src, io.w, io.h, fx, fy, nullptr);
+		val = stage_at<SHARPENER>(io, io.w, io.h, fx, fy, k);
 	}
 	st_rgba16f(io.dst, x, y, val);
 }
@@ -110,7 +126,17 @@ cudaError_t launch_cas(const PostImg& io, const TaaCasPush& pc, cudaStream_t str
 }
 cudaError_t launch_post_process(const PostImg& io, const TaaPostProcessPush& pc, cudaStream_t stream) {
 	dim3 b(32, 8);
-	post_process_kernel<<<grid2d(io.w, io.h, b), b, 0, stream>>>(io, pc);
+	post_process_kernel<0><<<grid2d(io.w, io.h, b), b, 0, stream>>>(io, pc, 0.f);
+	return cudaGetLastError();
+}
+cudaError_t launch_sharpen_post(const PostImg& io, int sharpener, float sharpeningFactor, const TaaCasPush& cas, const TaaPostProcessPush& pc, cudaStream_t stream) {
+	dim3 b(32, 8);
+	if (sharpener == 1) post_process_kernel<1><<<grid2d(io.w, io.h, b), b, 0, stream>>>(io, pc, sharpeningFactor);
+	else {
+		float peak;
+		memcpy(&peak, &cas.const1[0], 4);
+		post_process_kernel<2><<<grid2d(io.w, io.h, b), b, 0, stream>>>(io, pc, peak);
+	}
 	return cudaGetLastError();
 }
 
