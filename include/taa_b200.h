@@ -41,7 +41,7 @@ extern "C" {
 #define TAA_API __attribute__((visibility("default")))
 #endif
 
-#define TAA_B200_ABI_VERSION 1
+#define TAA_B200_ABI_VERSION 2
 
 /* ---- status codes (replace the reference's C++ exceptions, avk.cpp:5520 / main.cpp:5074) ---- */
 enum {
@@ -208,6 +208,9 @@ typedef struct taa_post_chain {
 	TaaCasPush         cas;                /* used if sharpener == 2 (fill with taa_cas_setup) */
 	int32_t            postprocess;        /* mPostProcessEnabled (taa.hpp:1352) */
 	TaaPostProcessPush pp;                 /* used if postprocess != 0 */
+	int32_t            fxaa;               /* run FXAA on the pixels the seg-mask marks (taa.hpp:1061: mRayTraceAugmentFlags & TAA_RTFLAG_FXA);
+	                                          needs images->segmask; runs before the sharpener like in render() */
+	TaaFxaaPush        fxaa_pc;            /* used if fxaa != 0 (fill with taa_fxaa_default) */
 } taa_post_chain;
 
 /* ---- context ---- */
@@ -262,7 +265,7 @@ TAA_API int taa_resolve_ex(taa_ctx* ctx, const taa_resolve_images* images, const
 
 /*
  * taa_frame — taa.comp plus the follow-on passes of render() (taa.hpp:1111-1159) in one call:
- * resolve -> [sharpen | CAS] -> [post-process]; `final` receives the image render() would blit to
+ * resolve -> [FXAA] -> [sharpen | CAS] -> [post-process]; `final` receives the image render() would blit to
  * the swapchain (taa.hpp:1161-1169). images->result may be NULL when a sharpener or post-process
  * consumes it (fused path keeps it on chip).
  */
@@ -274,6 +277,14 @@ TAA_API int taa_sharpen(taa_ctx* ctx, const taa_image* src, const taa_image* dst
 TAA_API int taa_sharpen_cas(taa_ctx* ctx, const taa_image* src, const taa_image* dst, const TaaCasPush* pc, void* stream);       /* sharpen_cas.comp, taa.hpp:1126-1135 */
 TAA_API int taa_post_process(taa_ctx* ctx, const taa_image* src, const taa_image* debug, const taa_image* dst,
                              const TaaPostProcessPush* pc, void* stream);                                                       /* post_process.comp, taa.hpp:1141-1159 */
+
+/* the FXAA branch (taa.hpp:1061-1107). `segmask` is the r32ui image taa.comp wrote (bits 0-1 == 1 marks a pixel for FXAA). */
+TAA_API int taa_fxaa_prepare(taa_ctx* ctx, const taa_image* src, const taa_image* dst, void* stream);                            /* antialias_fxaa_prepare.comp, taa.hpp:1068-1075 */
+TAA_API int taa_fxaa(taa_ctx* ctx, const taa_image* src_prepared, const taa_image* segmask, const taa_image* dst,
+                     const TaaFxaaPush* pc, void* stream);                                                                      /* antialias_fxaa.comp, taa.hpp:1086-1094 */
+/* both dispatches in one launch: reads the screen result itself, bit-identical to taa_fxaa_prepare + taa_fxaa */
+TAA_API int taa_fxaa_fused(taa_ctx* ctx, const taa_image* src, const taa_image* segmask, const taa_image* dst,
+                           const TaaFxaaPush* pc, void* stream);
 
 /* number of CUDA kernels launched through this context so far (bench.py reports it as gpu_launches) */
 TAA_API long long taa_launch_count(const taa_ctx* ctx);
@@ -294,6 +305,8 @@ TAA_API void taa_cas_setup(TaaCasPush* out, float sharpness, float out_width, fl
 TAA_API void taa_parameters_default(TaaParameters* out);
 /* uniforms defaults: identity matrices, both param sets default, everything else zero */
 TAA_API void taa_uniforms_default(TaaUniforms* out);
+/* push_constants_for_fxaa defaults (taa.hpp:93-99) with fxaaQualityRcpFrame = 1 / (w, h) as update() sets it (taa.hpp:953) */
+TAA_API void taa_fxaa_default(TaaFxaaPush* out, int32_t w, int32_t h);
 /* push_constants_for_postprocess defaults as initialised at taa.hpp:352-359 for a w x h target */
 TAA_API void taa_postprocess_default(TaaPostProcessPush* out, int32_t w, int32_t h);
 

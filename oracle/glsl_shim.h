@@ -1,6 +1,6 @@
 /*
  * glsl_shim.h — just enough GLSL 4.60 compute semantics in C++17 to compile the REFERENCE's own shader sources
- * (shaders/taa.comp, sharpen.comp, post_process.comp, read where they lie under /root/reference by
+ * (shaders/taa.comp, sharpen.comp, post_process.comp, antialias_fxaa_prepare.comp, antialias_fxaa.comp + Fxaa3_11_mod.h, read where they lie under /root/reference by
  * oracle/ref_build.py) into oracle/_ref/libtaa_ref.so. TEST INFRASTRUCTURE, like everything under oracle/.
  *
  * This file holds no algorithm of the reference: it is the "GLSL machine" (vector types, built-ins, the sampler
@@ -48,11 +48,13 @@ struct vec2 {
 	vec2(const ivec2& v);  // GLSL implicit int -> float conversion
 	vec2(const vec2& o) : x(o.x), y(o.y) {}
 	vec2& operator=(const vec2& o) { x = o.x; y = o.y; return *this; }
+	vec2 _xy() const { return vec2(x, y); }
 };
 struct Swz2 {  // an l-value swizzle of two components
 	float &a, &b;
 	operator vec2() const { return vec2(a, b); }
 	Swz2& operator=(const vec2& v) { a = v.x; b = v.y; return *this; }
+	Swz2& operator=(const Swz2& o) { const float p = o.a, q = o.b; a = p; b = q; return *this; }
 	Swz2& operator+=(const vec2& v) { a = a + v.x; b = b + v.y; return *this; }
 	Swz2& operator+=(float v) { a = a + v; b = b + v; return *this; }
 };
@@ -76,6 +78,7 @@ struct Swz3 {
 	float &a, &b, &c;
 	operator vec3() const { return vec3(a, b, c); }
 	Swz3& operator=(const vec3& v) { a = v.x; b = v.y; c = v.z; return *this; }
+	Swz3& operator=(const Swz3& o) { const float p = o.a, q = o.b, r = o.c; a = p; b = q; c = r; return *this; }
 	Swz3& operator+=(const vec3& v) { a = a + v.x; b = b + v.y; c = c + v.z; return *this; }
 };
 struct vec4 {
@@ -261,8 +264,13 @@ typedef Image texture2D;
 typedef Image image2D;
 typedef Image uimage2D;
 struct sampler {};
-struct sampler2D_t { const Image* t; };
-inline sampler2D_t sampler2D(const Image& t, const sampler&) { return sampler2D_t{&t}; }
+struct sampler2D {  // `sampler2D(tex, smp)` (separate texture + sampler, taa.comp) or a combined binding that the harness points at an image
+	const Image* t = nullptr;
+	sampler2D() {}
+	sampler2D(const Image& tex, const sampler&) : t(&tex) {}
+};
+typedef sampler2D sampler2D_t;
+inline ivec2 textureSize(const sampler2D& s, int) { return ivec2(s.t->w, s.t->h); }
 inline ivec2 textureSize(const Image& t, int) { return ivec2(t.w, t.h); }
 inline ivec2 imageSize(const Image& t) { return ivec2(t.w, t.h); }
 
@@ -291,6 +299,30 @@ inline vec4 texture(const sampler2D_t& s, const vec2& uv) {
 	const int y0 = clampi(j0, 0, t.h - 1), y1 = clampi(j0 == 2147483647 ? j0 : j0 + 1, 0, t.h - 1);
 	return lerp4(lerp4(texel(t, x0, y0), texel(t, x1, y0), a), lerp4(texel(t, x0, y1), texel(t, x1, y1), a), b);
 }
+inline vec4 texelFetch(const sampler2D& s, const ivec2& c, int) { return texelFetch(*s.t, c, 0); }
+inline vec4 textureLod(const sampler2D_t& s, const vec2& uv, float) { return texture(s, uv); }
+// textureLodOffset: the texel offset is added to the footprint's integer coordinates before clamp-to-edge
+inline vec4 textureLodOffset(const sampler2D_t& s, const vec2& uv, float, const ivec2& o) {
+	const Image& t = *s.t;
+	const float u = uv.x * (float)t.w - 0.5f, v = uv.y * (float)t.h - 0.5f;
+	const float fu = std::floor(u), fv = std::floor(v);
+	const float a = u - fu, b = v - fv;
+	const int i0 = f2i(fu) + o.x, j0 = f2i(fv) + o.y;
+	const int x0 = clampi(i0, 0, t.w - 1), x1 = clampi(i0 + 1, 0, t.w - 1), y0 = clampi(j0, 0, t.h - 1), y1 = clampi(j0 + 1, 0, t.h - 1);
+	return lerp4(lerp4(texel(t, x0, y0), texel(t, x1, y0), a), lerp4(texel(t, x0, y1), texel(t, x1, y1), a), b);
+}
+// textureGather(Offset): the linear filter's 2x2 footprint, chosen after snapping the unnormalised coordinate to 1/256 texel
+// (subTexelPrecisionBits = 8), returned as (i0,j1), (i1,j1), (i1,j0), (i0,j0)
+inline vec4 textureGatherOffset(const sampler2D_t& s, const vec2& uv, const ivec2& o, int comp) {
+	const Image& t = *s.t;
+	const float u = uv.x * (float)t.w - 0.5f, v = uv.y * (float)t.h - 0.5f;
+	const float fu = std::floor(std::floor(u * 256.0f + 0.5f) * (1.0f / 256.0f)), fv = std::floor(std::floor(v * 256.0f + 0.5f) * (1.0f / 256.0f));
+	const int i0 = f2i(fu) + o.x, j0 = f2i(fv) + o.y;
+	const int x0 = clampi(i0, 0, t.w - 1), x1 = clampi(i0 + 1, 0, t.w - 1), y0 = clampi(j0, 0, t.h - 1), y1 = clampi(j0 + 1, 0, t.h - 1);
+	const vec4 a = texel(t, x0, y1), b = texel(t, x1, y1), c = texel(t, x1, y0), d = texel(t, x0, y0);
+	return vec4((&a.x)[comp], (&b.x)[comp], (&c.x)[comp], (&d.x)[comp]);
+}
+inline vec4 textureGather(const sampler2D_t& s, const vec2& uv, int comp) { return textureGatherOffset(s, uv, ivec2(0, 0), comp); }
 inline void imageStore(const Image& t, const ivec2& c, const vec4& v) {
 	if (!t.data || c.x < 0 || c.y < 0 || c.x >= t.w || c.y >= t.h) return;
 	uint16_t* q = (uint16_t*)(t.data + (long long)c.y * t.pitch) + 4 * c.x;

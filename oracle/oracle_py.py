@@ -41,6 +41,10 @@ def lib() -> C.CDLL:
         L.taa_oracle_cas_setup.argtypes = [P(C.c_uint32), P(C.c_uint32)] + [C.c_float] * 5
         L.taa_oracle_post_process.restype = C.c_int
         L.taa_oracle_post_process.argtypes = [P(abi.taa_image), P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int, P(abi.TaaPostProcessPush), C.c_int]
+        L.taa_oracle_fxaa_prepare.restype = C.c_int
+        L.taa_oracle_fxaa_prepare.argtypes = [P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int, C.c_int]
+        L.taa_oracle_fxaa.restype = C.c_int
+        L.taa_oracle_fxaa.argtypes = [P(abi.taa_image), P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int, P(abi.TaaFxaaPush), C.c_int, C.c_int]
         L.taa_oracle_halton.restype = C.c_float
         L.taa_oracle_halton.argtypes = [C.c_int, C.c_int]
         L.taa_oracle_jitter.restype = C.c_int
@@ -72,6 +76,11 @@ def ref_lib() -> C.CDLL:
         L.taa_ref_sharpen.argtypes = [P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int, C.c_float]
         L.taa_ref_post_process.restype = C.c_int
         L.taa_ref_post_process.argtypes = [P(abi.taa_image), P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int, P(abi.TaaPostProcessPush)]
+        L.taa_ref_fxaa_prepare.restype = C.c_int
+        L.taa_ref_fxaa_prepare.argtypes = [P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int]
+        for f in (L.taa_ref_fxaa_gather4, L.taa_ref_fxaa_offset):
+            f.restype = C.c_int
+            f.argtypes = [P(abi.taa_image), P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int, P(abi.TaaFxaaPush)]
         _ref = L
     return _ref
 
@@ -158,6 +167,39 @@ def post_process(src, debug, pc: abi.TaaPostProcessPush, nthreads=0):
     dst = np.zeros_like(src)
     a, b, d = _img(src), _img(dst), _img(debug)
     assert lib().taa_oracle_post_process(C.byref(a), C.byref(d) if debug is not None else None, C.byref(b), w, h, C.byref(pc), nthreads) == 0
+    return dst
+
+
+def fxaa_push(w, h, subpix=0.75, edge_threshold=0.116, edge_threshold_min=0.0833):
+    """push_constants_for_fxaa as update() fills it (taa.hpp:93-99, 953): rcpFrame = 1 / output resolution, in fp32."""
+    pc = abi.TaaFxaaPush()
+    pc.fxaaQualityRcpFrame[0] = np.float32(1.0) / np.float32(w)
+    pc.fxaaQualityRcpFrame[1] = np.float32(1.0) / np.float32(h)
+    pc.fxaaQualitySubpix, pc.fxaaQualityEdgeThreshold, pc.fxaaQualityEdgeThresholdMin = subpix, edge_threshold, edge_threshold_min
+    return pc
+
+
+def fxaa_prepare(src, nthreads=0, impl="oracle"):
+    h, w = src.shape[:2]
+    dst = np.zeros_like(src)
+    a, b = _img(src), _img(dst)
+    if impl == "ref":
+        assert ref_lib().taa_ref_fxaa_prepare(C.byref(a), C.byref(b), w, h) == 0
+    else:
+        assert lib().taa_oracle_fxaa_prepare(C.byref(a), C.byref(b), w, h, nthreads) == 0
+    return dst
+
+
+def fxaa(src, segmask, pc: abi.TaaFxaaPush, gather4=True, nthreads=0, impl="oracle"):
+    """antialias_fxaa.comp on an image prepared by fxaa_prepare (luma in alpha)."""
+    h, w = src.shape[:2]
+    dst = np.zeros_like(src)
+    a, b, m = _img(src), _img(dst), _img(segmask)
+    if impl == "ref":
+        f = ref_lib().taa_ref_fxaa_gather4 if gather4 else ref_lib().taa_ref_fxaa_offset
+        assert f(C.byref(a), C.byref(m), C.byref(b), w, h, C.byref(pc)) == 0
+    else:
+        assert lib().taa_oracle_fxaa(C.byref(a), C.byref(m), C.byref(b), w, h, C.byref(pc), 1 if gather4 else 0, nthreads) == 0
     return dst
 
 

@@ -10,6 +10,8 @@
  *   shaders/sharpen_cas.comp         — main():30-53, with shaders/ffx_cas.h:375-394 (CasSetup),
  *                                      :408-537 (CasFilter, noScaling branch) and shaders/ffx_a.h:1455-1457
  *   shaders/post_process.comp        — main():29-88
+ *   shaders/antialias_fxaa_prepare.comp:15-26, shaders/antialias_fxaa.comp:30-64 with
+ *                                      shaders/Fxaa3_11_mod.h:433-440 (preset 12), :884-1243 (FxaaPixelShader, PC quality)
  *   source/helper_functions.hpp:9-26 — halton / halton_2_3
  *   source/taa.hpp:150-233           — get_jitter_offset_for_frame
  *
@@ -1039,6 +1041,185 @@ int taa_oracle_post_process(const taa_image* src, const taa_image* debug, const 
 			store_rgba16f(*dst, x, y, val);
 		}
 	}
+	(void)nthreads;
+	return TAA_OK;
+}
+
+// antialias_fxaa_prepare.comp:15-26: rgb copied, alpha = luma (stored as fp16 like every rgba16f texel)
+int taa_oracle_fxaa_prepare(const taa_image* src, const taa_image* dst, int w, int h, int nthreads) {
+	if (!src || !dst || !src->data || !dst->data) return TAA_E_INVALID_ARG;
+	Tex in = mkTex(*src, w, h);
+#ifdef _OPENMP
+	if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+#endif
+	for (int y = 0; y < h; ++y)
+		for (int x = 0; x < w; ++x) {
+			vec3 c = rgb(fetch_rgba16f(in, x, y));
+			store_rgba16f(*dst, x, y, mkvec4(c, dot(c, vec3{0.299f, 0.587f, 0.114f})));
+		}
+	(void)nthreads;
+	return TAA_OK;
+}
+
+} // extern "C" (reopened below)
+
+namespace {
+// textureLodOffset(tex, p, 0, o): the integer offset is added to the footprint's texel indices before clamp-to-edge
+inline vec4 sample_rgba16f_off(const Tex& t, vec2 uv, int ox, int oy) {
+	float u = uv.x * (float)t.w - 0.5f, v = uv.y * (float)t.h - 0.5f;
+	float fu = floorf(u), fv = floorf(v);
+	float a = u - fu, b = v - fv;
+	int i0 = f2i(fu) + ox, j0 = f2i(fv) + oy;
+	int x0 = iclamp(i0, 0, t.w - 1), x1 = iclamp(i0 + 1, 0, t.w - 1), y0 = iclamp(j0, 0, t.h - 1), y1 = iclamp(j0 + 1, 0, t.h - 1);
+	return lerp4(lerp4(fetch_rgba16f(t, x0, y0), fetch_rgba16f(t, x1, y0), a), lerp4(fetch_rgba16f(t, x0, y1), fetch_rgba16f(t, x1, y1), a), b);
+}
+// textureGather(Offset)(tex, p, comp = 3). The 2x2 footprint is the linear filter's; FXAA gathers AT a texel centre, where
+// floor(u) flips with the last bit of the coordinate. Like hardware samplers (VkPhysicalDeviceLimits::subTexelPrecisionBits = 8
+// on every desktop driver and on lavapipe) the unnormalised coordinate is snapped to 1/256 texel before the footprint is chosen.
+// Returned order (Vulkan spec, "Texel Gathering"): x = (i0,j1), y = (i1,j1), z = (i1,j0), w = (i0,j0).
+inline vec4 gather_alpha(const Tex& t, vec2 uv, int ox, int oy) {
+	float u = uv.x * (float)t.w - 0.5f, v = uv.y * (float)t.h - 0.5f;
+	float fu = floorf(floorf(u * 256.0f + 0.5f) * (1.0f / 256.0f)), fv = floorf(floorf(v * 256.0f + 0.5f) * (1.0f / 256.0f));
+	int i0 = f2i(fu) + ox, j0 = f2i(fv) + oy;
+	int x0 = iclamp(i0, 0, t.w - 1), x1 = iclamp(i0 + 1, 0, t.w - 1), y0 = iclamp(j0, 0, t.h - 1), y1 = iclamp(j0 + 1, 0, t.h - 1);
+	return {fetch_rgba16f(t, x0, y1).w, fetch_rgba16f(t, x1, y1).w, fetch_rgba16f(t, x1, y0).w, fetch_rgba16f(t, x0, y0).w};
+}
+
+// FxaaPixelShader, FXAA_PC == 1, FXAA_QUALITY_PRESET 12, FXAA_DISCARD 0, FXAA_GREEN_AS_LUMA 0 (Fxaa3_11_mod.h:433-440, 884-1243;
+// configured at antialias_fxaa.comp:23-27). gather4 selects the FXAA_GATHER4_ALPHA == 1 variant (:888-912), which is what a
+// GLSL front end that predefines GL_ARB_gpu_shader5 (glslang does) compiles; 0 = the textureLodOffset variant (:913-925, 946-951).
+// The nested doneNP blocks of the header (:1030-1190) are one loop over the step table here.
+vec4 fxaa_pixel(const Tex& tex, vec2 pos, vec2 rcpFrame, float subpix, float edgeThreshold, float edgeThresholdMin, bool gather4) {
+	static const float P[5] = {1.0f, 1.5f, 2.0f, 4.0f, 12.0f};  // FXAA_QUALITY_P0..P4, FXAA_QUALITY_PS = 5
+	vec2 posM = pos;
+	vec4 rgbyM = sample_rgba16f(tex, posM);
+	const float lumaM = rgbyM.w;
+	float lumaS, lumaE, lumaN, lumaW, lumaNW = 0, lumaSE = 0, lumaNE, lumaSW;
+	if (gather4) {
+		vec4 A = gather_alpha(tex, posM, 0, 0), B = gather_alpha(tex, posM, -1, -1);
+		lumaE = A.z; lumaS = A.x; lumaSE = A.y; lumaNW = B.w; lumaN = B.z; lumaW = B.x;
+	} else {
+		lumaS = sample_rgba16f_off(tex, posM, 0, 1).w;
+		lumaE = sample_rgba16f_off(tex, posM, 1, 0).w;
+		lumaN = sample_rgba16f_off(tex, posM, 0, -1).w;
+		lumaW = sample_rgba16f_off(tex, posM, -1, 0).w;
+	}
+	float maxSM = gmax(lumaS, lumaM), minSM = gmin(lumaS, lumaM);
+	float maxESM = gmax(lumaE, maxSM), minESM = gmin(lumaE, minSM);
+	float maxWN = gmax(lumaN, lumaW), minWN = gmin(lumaN, lumaW);
+	float rangeMax = gmax(maxWN, maxESM), rangeMin = gmin(minWN, minESM);
+	float rangeMaxScaled = rangeMax * edgeThreshold;
+	float range = rangeMax - rangeMin;
+	float rangeMaxClamped = gmax(edgeThresholdMin, rangeMaxScaled);
+	if (range < rangeMaxClamped) return rgbyM;  // earlyExit
+	if (gather4) {
+		lumaNE = sample_rgba16f_off(tex, posM, 1, -1).w;
+		lumaSW = sample_rgba16f_off(tex, posM, -1, 1).w;
+	} else {
+		lumaNW = sample_rgba16f_off(tex, posM, -1, -1).w;
+		lumaSE = sample_rgba16f_off(tex, posM, 1, 1).w;
+		lumaNE = sample_rgba16f_off(tex, posM, 1, -1).w;
+		lumaSW = sample_rgba16f_off(tex, posM, -1, 1).w;
+	}
+	float lumaNS = lumaN + lumaS, lumaWE = lumaW + lumaE;
+	float subpixRcpRange = 1.0f / range;
+	float subpixNSWE = lumaNS + lumaWE;
+	float edgeHorz1 = (-2.0f * lumaM) + lumaNS, edgeVert1 = (-2.0f * lumaM) + lumaWE;
+	float lumaNESE = lumaNE + lumaSE, lumaNWNE = lumaNW + lumaNE;
+	float edgeHorz2 = (-2.0f * lumaE) + lumaNESE, edgeVert2 = (-2.0f * lumaN) + lumaNWNE;
+	float lumaNWSW = lumaNW + lumaSW, lumaSWSE = lumaSW + lumaSE;
+	float edgeHorz4 = (fabsf(edgeHorz1) * 2.0f) + fabsf(edgeHorz2), edgeVert4 = (fabsf(edgeVert1) * 2.0f) + fabsf(edgeVert2);
+	float edgeHorz3 = (-2.0f * lumaW) + lumaNWSW, edgeVert3 = (-2.0f * lumaS) + lumaSWSE;
+	float edgeHorz = fabsf(edgeHorz3) + edgeHorz4, edgeVert = fabsf(edgeVert3) + edgeVert4;
+	float subpixNWSWNESE = lumaNWSW + lumaNESE;
+	float lengthSign = rcpFrame.x;
+	bool horzSpan = edgeHorz >= edgeVert;
+	float subpixA = subpixNSWE * 2.0f + subpixNWSWNESE;
+	if (!horzSpan) lumaN = lumaW;
+	if (!horzSpan) lumaS = lumaE;
+	if (horzSpan) lengthSign = rcpFrame.y;
+	float subpixB = (subpixA * (1.0f / 12.0f)) - lumaM;
+	float gradientN = lumaN - lumaM, gradientS = lumaS - lumaM;
+	float lumaNN = lumaN + lumaM, lumaSS = lumaS + lumaM;
+	bool pairN = fabsf(gradientN) >= fabsf(gradientS);
+	float gradient = gmax(fabsf(gradientN), fabsf(gradientS));
+	if (pairN) lengthSign = -lengthSign;
+	float subpixC = gclamp(fabsf(subpixB) * subpixRcpRange, 0.0f, 1.0f);
+	vec2 posB = posM;
+	vec2 offNP = {(!horzSpan) ? 0.0f : rcpFrame.x, horzSpan ? 0.0f : rcpFrame.y};
+	if (!horzSpan) posB.x += lengthSign * 0.5f;
+	if (horzSpan) posB.y += lengthSign * 0.5f;
+	vec2 posN = {posB.x - offNP.x * P[0], posB.y - offNP.y * P[0]};
+	vec2 posP = {posB.x + offNP.x * P[0], posB.y + offNP.y * P[0]};
+	float subpixD = ((-2.0f) * subpixC) + 3.0f;
+	float lumaEndN = sample_rgba16f(tex, posN).w;
+	float subpixE = subpixC * subpixC;
+	float lumaEndP = sample_rgba16f(tex, posP).w;
+	if (!pairN) lumaNN = lumaSS;
+	float gradientScaled = gradient * 1.0f / 4.0f;
+	float lumaMM = lumaM - lumaNN * 0.5f;
+	float subpixF = subpixD * subpixE;
+	bool lumaMLTZero = lumaMM < 0.0f;
+	lumaEndN -= lumaNN * 0.5f;
+	lumaEndP -= lumaNN * 0.5f;
+	bool doneN = fabsf(lumaEndN) >= gradientScaled, doneP = fabsf(lumaEndP) >= gradientScaled;
+	for (int i = 1;; ++i) {
+		if (!doneN) { posN.x -= offNP.x * P[i]; posN.y -= offNP.y * P[i]; }
+		bool doneNP = (!doneN) || (!doneP);
+		if (!doneP) { posP.x += offNP.x * P[i]; posP.y += offNP.y * P[i]; }
+		if (!doneNP || i == 4) break;
+		if (!doneN) lumaEndN = sample_rgba16f(tex, posN).w;
+		if (!doneP) lumaEndP = sample_rgba16f(tex, posP).w;
+		if (!doneN) lumaEndN = lumaEndN - lumaNN * 0.5f;
+		if (!doneP) lumaEndP = lumaEndP - lumaNN * 0.5f;
+		doneN = fabsf(lumaEndN) >= gradientScaled;
+		doneP = fabsf(lumaEndP) >= gradientScaled;
+	}
+	float dstN = posM.x - posN.x, dstP = posP.x - posM.x;
+	if (!horzSpan) dstN = posM.y - posN.y;
+	if (!horzSpan) dstP = posP.y - posM.y;
+	bool goodSpanN = (lumaEndN < 0.0f) != lumaMLTZero;
+	float spanLength = dstP + dstN;
+	bool goodSpanP = (lumaEndP < 0.0f) != lumaMLTZero;
+	float spanLengthRcp = 1.0f / spanLength;
+	bool directionN = dstN < dstP;
+	float dst = gmin(dstN, dstP);
+	bool goodSpan = directionN ? goodSpanN : goodSpanP;
+	float subpixG = subpixF * subpixF;
+	float pixelOffset = (dst * (-spanLengthRcp)) + 0.5f;
+	float subpixH = subpixG * subpix;
+	float pixelOffsetGood = goodSpan ? pixelOffset : 0.0f;
+	float pixelOffsetSubpix = gmax(pixelOffsetGood, subpixH);
+	if (!horzSpan) posM.x += pixelOffsetSubpix * lengthSign;
+	if (horzSpan) posM.y += pixelOffsetSubpix * lengthSign;
+	return mkvec4(rgb(sample_rgba16f(tex, posM)), lumaM);
+}
+}  // namespace
+
+extern "C" {
+
+// antialias_fxaa.comp:30-64: pixels whose seg-mask says 1 (FXAA) run FxaaPixelShader on the prepared image (luma in alpha), all
+// others are copied. gather4: see fxaa_pixel.
+int taa_oracle_fxaa(const taa_image* src, const taa_image* segmask, const taa_image* dst, int w, int h, const TaaFxaaPush* pc, int gather4, int nthreads) {
+	if (!src || !segmask || !dst || !pc || !src->data || !segmask->data || !dst->data) return TAA_E_INVALID_ARG;
+	Tex in = mkTex(*src, w, h), seg = mkTex(*segmask, w, h);
+#ifdef _OPENMP
+	if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+#endif
+	for (int y = 0; y < h; ++y)
+		for (int x = 0; x < w; ++x) {
+			vec4 color;
+			if ((fetch_r32ui(seg, x, y) & 3u) == 1u) {
+				vec2 rcp = {pc->fxaaQualityRcpFrame[0], pc->fxaaQualityRcpFrame[1]};
+				color = fxaa_pixel(in, (toVec2(ivec2{x, y}) + 0.5f) * rcp, rcp, pc->fxaaQualitySubpix, pc->fxaaQualityEdgeThreshold, pc->fxaaQualityEdgeThresholdMin,
+				                   gather4 != 0);
+			} else {
+				color = fetch_rgba16f(in, x, y);
+			}
+			store_rgba16f(*dst, x, y, color);
+		}
 	(void)nthreads;
 	return TAA_OK;
 }

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 TAA_OK, TAA_E_INVALID_ARG, TAA_E_UNSUPPORTED, TAA_E_CUDA, TAA_E_NCCL, TAA_E_HALO_OVERFLOW = 0, -1, -2, -3, -4, -5
 TAA_FLAG_DEFAULT, TAA_FLAG_EXACT, TAA_FLAG_FIXUP_ALL = 0, 1, 2
@@ -80,7 +80,8 @@ class taa_resolve_images(C.Structure):
 
 
 class taa_post_chain(C.Structure):
-    _fields_ = [("sharpener", _i32), ("sharpen", TaaSharpenPush), ("cas", TaaCasPush), ("postprocess", _i32), ("pp", TaaPostProcessPush)]
+    _fields_ = [("sharpener", _i32), ("sharpen", TaaSharpenPush), ("cas", TaaCasPush), ("postprocess", _i32), ("pp", TaaPostProcessPush),
+                ("fxaa", _i32), ("fxaa_pc", TaaFxaaPush)]
 
 
 class taa_desc(C.Structure):
@@ -122,6 +123,10 @@ SIGNATURES = {
     "taa_sharpen": (C.c_int, [_vp, _P(taa_image), _P(taa_image), _P(TaaSharpenPush), _vp]),
     "taa_sharpen_cas": (C.c_int, [_vp, _P(taa_image), _P(taa_image), _P(TaaCasPush), _vp]),
     "taa_post_process": (C.c_int, [_vp, _P(taa_image), _P(taa_image), _P(taa_image), _P(TaaPostProcessPush), _vp]),
+    "taa_fxaa_prepare": (C.c_int, [_vp, _P(taa_image), _P(taa_image), _vp]),
+    "taa_fxaa": (C.c_int, [_vp, _P(taa_image), _P(taa_image), _P(taa_image), _P(TaaFxaaPush), _vp]),
+    "taa_fxaa_fused": (C.c_int, [_vp, _P(taa_image), _P(taa_image), _P(taa_image), _P(TaaFxaaPush), _vp]),
+    "taa_fxaa_default": (None, [_P(TaaFxaaPush), _i32, _i32]),
     "taa_launch_count": (_ll, [_vp]),
     "taa_poll_status": (C.c_int, [_vp, _vp]),
     "taa_fixup_pixels": (_ll, [_vp, _vp]),

@@ -268,58 +268,91 @@ int taa_post_process(taa_ctx* c, const taa_image* src, const taa_image* debug, c
 	return TAA_OK;
 }
 
+static int make_fxaa(taa_ctx* c, const taa_image* src, const taa_image* seg, const taa_image* dst, const TaaFxaaPush* pc, PostImg& io) {
+	if (!pc || !seg || !seg->data) { set_error(c, "fxaa: push constants and the segmentation mask are required"); return TAA_E_INVALID_ARG; }
+	int r = make_post(c, src, nullptr, dst, io);
+	if (r == TAA_OK) r = check_pitch(c, *seg, c->desc.out_width, 4, "segmask");
+	if (r != TAA_OK) return r;
+	fill_img(io.debug, *seg, c->desc.out_height);
+	return TAA_OK;
+}
+int taa_fxaa_prepare(taa_ctx* c, const taa_image* src, const taa_image* dst, void* stream) {
+	PostImg io;
+	int r = make_post(c, src, nullptr, dst, io);
+	if (r != TAA_OK) return r;
+	cudaError_t e = launch_fxaa_prepare(io, (cudaStream_t)stream);
+	if (e != cudaSuccess) return cuda_fail(c, e, "fxaa_prepare launch");
+	c->launches++;
+	return TAA_OK;
+}
+static int fxaa_impl(taa_ctx* c, const taa_image* src, const taa_image* seg, const taa_image* dst, const TaaFxaaPush* pc, bool prepared, void* stream) {
+	PostImg io;
+	int r = make_fxaa(c, src, seg, dst, pc, io);
+	if (r != TAA_OK) return r;
+	cudaError_t e = launch_fxaa(io, *pc, prepared, (cudaStream_t)stream);
+	if (e != cudaSuccess) return cuda_fail(c, e, "fxaa launch");
+	c->launches++;
+	return TAA_OK;
+}
+int taa_fxaa(taa_ctx* c, const taa_image* src, const taa_image* seg, const taa_image* dst, const TaaFxaaPush* pc, void* stream) {
+	return fxaa_impl(c, src, seg, dst, pc, true, stream);
+}
+int taa_fxaa_fused(taa_ctx* c, const taa_image* src, const taa_image* seg, const taa_image* dst, const TaaFxaaPush* pc, void* stream) {
+	return fxaa_impl(c, src, seg, dst, pc, false, stream);
+}
+
+// render() after taa.comp (taa.hpp:1029-1169): [fxaa_prepare + fxaa] -> [sharpen | CAS] -> [post-process]. Each arrow of the reference is a
+// full-frame image; here FXAA is one launch and the sharpener is evaluated inside the post-process launch.
 int taa_frame(taa_ctx* c, const taa_resolve_images* images, const TaaUniforms* u, const taa_post_chain* chain, const taa_image* final_img, void* stream) {
 	if (!c || !images || !u || !chain || !final_img || !final_img->data) { set_error(c, "taa_frame: NULL argument"); return TAA_E_INVALID_ARG; }
 	const taa_desc& d = c->desc;
-	const bool sharpen = chain->sharpener != 0, post = chain->postprocess != 0;
+	const bool fxaa = chain->fxaa != 0, sharpen = chain->sharpener != 0, post = chain->postprocess != 0;
 	if (chain->sharpener < 0 || chain->sharpener > 2) { set_error(c, "mSharpener must be 0, 1 or 2 (taa.hpp:1418)"); return TAA_E_INVALID_ARG; }
+	if (fxaa && !images->segmask.data) { set_error(c, "taa_frame: FXAA needs the segmentation mask image (mRayTraceAugment)"); return TAA_E_INVALID_ARG; }
+	if (post && (chain->pp.debugL_show || chain->pp.debugR_show) && !images->debug.data) { set_error(c, "post_process: debug image required when debug*_show is set"); return TAA_E_INVALID_ARG; }
 	taa_resolve_images im = *images;
 	const int64_t pitch = (int64_t)d.out_width * 8;
-	// stage 0: resolve. Its screen result goes to the caller's image, or to `final` when nothing follows, or to scratch.
-	if (!sharpen && !post) {
-		if (!im.result.data) im.result = *final_img;
-	} else if (!im.result.data) {
-		int r = ensure_scratch(c, 0);
+	int stages = (fxaa ? 1 : 0) + ((sharpen || post) ? 1 : 0);  // launches after the resolve
+	int next_scratch = 0;
+	auto scratch = [&](taa_image& out) -> int {
+		int r = ensure_scratch(c, next_scratch);
 		if (r != TAA_OK) return r;
-		im.result = {c->scratch[0], pitch, 0, d.out_height};
+		out = {c->scratch[next_scratch], pitch, 0, d.out_height};
+		next_scratch ^= 1;
+		return TAA_OK;
+	};
+	// stage 0: resolve. Its screen result goes to the caller's image, or to `final` when nothing follows, or to scratch.
+	if (!im.result.data) {
+		if (stages == 0) im.result = *final_img;
+		else { int r = scratch(im.result); if (r != TAA_OK) return r; }
 	}
 	int r = taa_resolve_ex(c, &im, u, stream);
 	if (r != TAA_OK) return r;
 	taa_image last = im.result;
-	if (!sharpen && !post) {
-		if (last.data != final_img->data) {  // caller wanted both: plain copy (the reference would blit, taa.hpp:1169)
-			cudaError_t e = cudaMemcpy2DAsync(final_img->data, final_img->pitch_bytes, last.data, last.pitch_bytes, (size_t)d.out_width * 8, d.out_height,
-			                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-			if (e != cudaSuccess) return cuda_fail(c, e, "copy result -> final");
-		}
-		return TAA_OK;
+	if (fxaa) {
+		taa_image dst = *final_img;
+		if (--stages > 0) { r = scratch(dst); if (r != TAA_OK) return r; }
+		r = taa_fxaa_fused(c, &last, &im.segmask, &dst, &chain->fxaa_pc, stream);
+		if (r != TAA_OK) return r;
+		last = dst;
 	}
 	if (sharpen && post) {  // [sharpen | CAS] evaluated inside the post-process pass: one launch, no intermediate image
-		if ((chain->pp.debugL_show || chain->pp.debugR_show) && !images->debug.data) { set_error(c, "post_process: debug image required when debug*_show is set"); return TAA_E_INVALID_ARG; }
 		PostImg io;
 		r = make_post(c, &last, images->debug.data ? &images->debug : nullptr, final_img, io);
 		if (r != TAA_OK) return r;
 		cudaError_t e = launch_sharpen_post(io, chain->sharpener, chain->sharpen.sharpeningFactor, chain->cas, chain->pp, (cudaStream_t)stream);
 		if (e != cudaSuccess) return cuda_fail(c, e, "sharpen + post_process launch");
 		c->launches++;
-		return TAA_OK;
-	}
-	if (sharpen) {
-		taa_image dst;
-		if (post) {
-			r = ensure_scratch(c, 1);
-			if (r != TAA_OK) return r;
-			dst = {c->scratch[1], pitch, 0, d.out_height};
-		} else {
-			dst = *final_img;
-		}
-		r = chain->sharpener == 1 ? taa_sharpen(c, &last, &dst, &chain->sharpen, stream) : taa_sharpen_cas(c, &last, &dst, &chain->cas, stream);
+	} else if (sharpen) {
+		r = chain->sharpener == 1 ? taa_sharpen(c, &last, final_img, &chain->sharpen, stream) : taa_sharpen_cas(c, &last, final_img, &chain->cas, stream);
 		if (r != TAA_OK) return r;
-		last = dst;
-	}
-	if (post) {
+	} else if (post) {
 		r = taa_post_process(c, &last, images->debug.data ? &images->debug : nullptr, final_img, &chain->pp, stream);
 		if (r != TAA_OK) return r;
+	} else if (last.data != final_img->data) {  // caller wanted both: plain copy (the reference would blit, taa.hpp:1169)
+		cudaError_t e = cudaMemcpy2DAsync(final_img->data, final_img->pitch_bytes, last.data, last.pitch_bytes, (size_t)d.out_width * 8, d.out_height,
+		                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+		if (e != cudaSuccess) return cuda_fail(c, e, "copy result -> final");
 	}
 	return TAA_OK;
 }
@@ -407,6 +440,16 @@ void taa_uniforms_default(TaaUniforms* u) {
 	for (int i = 0; i < 4; ++i) u->mHistoryViewProjMatrix[i * 5] = u->mInverseViewProjMatrix[i * 5] = 1.0f;
 	taa_parameters_default(&u->param[0]);
 	taa_parameters_default(&u->param[1]);
+}
+
+void taa_fxaa_default(TaaFxaaPush* pc, int32_t w, int32_t h) {  // taa.hpp:93-99, 953
+	if (!pc) return;
+	memset(pc, 0, sizeof *pc);
+	pc->fxaaQualityRcpFrame[0] = 1.f / (float)w;
+	pc->fxaaQualityRcpFrame[1] = 1.f / (float)h;
+	pc->fxaaQualitySubpix = 0.75f;
+	pc->fxaaQualityEdgeThreshold = 0.116f;
+	pc->fxaaQualityEdgeThresholdMin = 0.0833f;
 }
 
 void taa_postprocess_default(TaaPostProcessPush* pp, int32_t w, int32_t h) {  // taa.hpp:101-111, 352-359

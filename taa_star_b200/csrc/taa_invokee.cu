@@ -321,10 +321,15 @@ static int render_with_sources(taa_invokee* t, int64_t frame, const std::vector<
 		chain.cas = t->mCasPushConstants;
 		chain.postprocess = t->S.mPostProcessEnabled ? 1 : 0;
 		chain.pp = t->mPostProcessPushConstants;
+		// FXAA on the pixels the seg-mask marks (taa.hpp:1033, 1061). The sparse ray-trace callback between the two (taa.hpp:1036-1058)
+		// belongs to the ray tracer and is out of scope: pixels marked 2 keep their TAA colour.
+		chain.fxaa = rt && ((t->mParameters[0].mRayTraceAugmentFlags & TAA_RTFLAG_FXA) || (t->S.mSplitScreen && (t->mParameters[1].mRayTraceAugmentFlags & TAA_RTFLAG_FXA)));
+		chain.fxaa_pc = t->mFxaaPushConstants;
 		// which image ends up on screen: result -> temp[0] (sharpener) -> postprocess (taa.hpp:1029-1161)
 		void* fin = t->img[TAA_IMG_RESULT][i];
 		if (chain.postprocess) fin = t->img[TAA_IMG_POSTPROCESS][i];
-		else if (chain.sharpener) fin = t->img[TAA_IMG_TEMP0][i];
+		else if (chain.sharpener) fin = t->img[chain.fxaa ? TAA_IMG_TEMP1 : TAA_IMG_TEMP0][i];
+		else if (chain.fxaa) fin = t->img[TAA_IMG_TEMP0][i];
 		taa_image fimg = whole(fin, W, H, 8);
 		r = taa_frame(t->ctx, &im, &U, &chain, &fimg, stream);
 		if (r != TAA_OK) { inv_error(t, "taa_frame: %s", taa_last_error_string(t->ctx)); return r; }

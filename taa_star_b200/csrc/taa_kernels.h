@@ -25,4 +25,9 @@ cudaError_t launch_post_process(const PostImg& io, const TaaPostProcessPush& pc,
 // [sharpen.comp | sharpen_cas.comp] -> post_process.comp in one pass: no intermediate image
 cudaError_t launch_sharpen_post(const PostImg& io, int sharpener, float sharpeningFactor, const TaaCasPush& cas, const TaaPostProcessPush& pc, cudaStream_t stream);
 
+// the FXAA branch (taa_fxaa.cu). io.debug carries the segmentation mask for launch_fxaa; prepared = the source's alpha already
+// holds the luma (antialias_fxaa_prepare.comp ran), else it is computed on the fly (both dispatches in one launch)
+cudaError_t launch_fxaa_prepare(const PostImg& io, cudaStream_t stream);
+cudaError_t launch_fxaa(const PostImg& io, const TaaFxaaPush& pc, bool prepared, cudaStream_t stream);
+
 }  // namespace taa

@@ -11,7 +11,7 @@ from typing import Dict, Optional, Sequence, Tuple, Union
 import torch
 
 from . import abi
-from .abi import (TaaCasPush, TaaError, TaaParameters, TaaPostProcessPush, TaaSharpenPush, TaaUniforms, taa_desc, taa_image,
+from .abi import (TaaCasPush, TaaError, TaaFxaaPush, TaaParameters, TaaPostProcessPush, TaaSharpenPush, TaaUniforms, taa_desc, taa_image,
                   taa_post_chain, taa_resolve_images, taa_source_views)
 
 # bytes per texel of every binding of taa.comp (shaders/shader_cpu_common.h:60-77)
@@ -119,6 +119,16 @@ class TaaContext:
         self._check(self._lib.taa_post_process(self._h, C.byref(a), C.byref(d) if debug is not None else None, C.byref(b), C.byref(pc),
                                                _stream_ptr(stream)), "taa_post_process")
 
+    def fxaa_prepare(self, src, dst, stream=None):
+        a, b = _image(src, 8), _image(dst, 8)
+        self._check(self._lib.taa_fxaa_prepare(self._h, C.byref(a), C.byref(b), _stream_ptr(stream)), "taa_fxaa_prepare")
+
+    def fxaa(self, src, segmask, dst, pc: TaaFxaaPush, fused: bool = False, stream=None):
+        """antialias_fxaa.comp on a prepared image; fused=True takes the unprepared screen result (prepare + fxaa in one launch)."""
+        a, m, b = _image(src, 8), _image(segmask, 4), _image(dst, 8)
+        f = self._lib.taa_fxaa_fused if fused else self._lib.taa_fxaa
+        self._check(f(self._h, C.byref(a), C.byref(m), C.byref(b), C.byref(pc), _stream_ptr(stream)), "taa_fxaa")
+
     def poll_status(self, stream=None) -> int:
         return self._lib.taa_poll_status(self._h, _stream_ptr(stream))
 
@@ -135,6 +145,13 @@ def cas_setup(sharpness: float, out_w: int, out_h: int) -> TaaCasPush:
     """CasSetup as update() calls it (taa.hpp:965)."""
     pc = TaaCasPush()
     abi.load_library().taa_cas_setup(C.byref(pc), sharpness, float(out_w), float(out_h))
+    return pc
+
+
+def fxaa_default(w: int, h: int) -> TaaFxaaPush:
+    """push_constants_for_fxaa as update() fills them (taa.hpp:93-99, 953)."""
+    pc = TaaFxaaPush()
+    abi.load_library().taa_fxaa_default(C.byref(pc), w, h)
     return pc
 
 

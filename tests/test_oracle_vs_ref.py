@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_py
-from common import mismatch_report, np_inputs, random_history
+from common import mismatch_report, np_inputs, random_history, bits16
 from taa_star_b200 import abi, configs, host
 from taa_star_b200.synth import SyntheticScene
 
@@ -157,3 +157,40 @@ def test_sharpen_and_post_process():
             setattr(pc, k, v)
         pc.debugR_mask[3] = 1.0
         assert mismatch_report(f"post_process {c}", oracle_py.ref_post_process(src, dbg, pc), oracle_py.post_process(src, dbg, pc)) is None
+
+
+def fxaa_test_image(h, w, seed):
+    """Hard edges at all orientations (long ones too, so that the end-of-edge search runs out its steps), thin lines, noise, flat areas."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.zeros((h, w, 4), np.float32)
+    img[..., 0] = (yy > 0.37 * xx + 3.3)                                   # shallow diagonal edge: long spans
+    img[..., 1] = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2 < (0.3 * h) ** 2)  # circle
+    img[..., 2] = (xx > 0.11 * yy + w / 3)                                 # steep diagonal
+    img[h // 2, :, :3] = 1.0                                               # 1-px horizontal line
+    img[:, w // 4, :3] = 0.0                                               # 1-px vertical line
+    img[: h // 6, : w // 3, :3] = rng.random((h // 6, w // 3, 3), dtype=np.float32)  # noise block
+    img[..., :3] = img[..., :3] * 0.8 + 0.1 * rng.random((h, w, 1), dtype=np.float32) * (yy[..., None] > 0.8 * h)
+    img[..., 3] = rng.random((h, w), dtype=np.float32)                     # garbage alpha: fxaa_prepare must overwrite it
+    return img.astype(np.float16)
+
+
+def test_fxaa_prepare_and_fxaa():
+    for (h, w, seed) in ((H, W, 31), (37, 53, 32), (1, 1, 33), (2, 64, 34)):
+        src = fxaa_test_image(h, w, seed)
+        prep = oracle_py.fxaa_prepare(src)
+        assert mismatch_report("fxaa_prepare", oracle_py.fxaa_prepare(src, impl="ref"), prep) is None
+        rng = np.random.default_rng(seed + 100)
+        seg_all = np.full((h, w), 1 | (5 << 16), np.uint32)
+        seg_mixed = rng.integers(0, 4, (h, w)).astype(np.uint32) | (rng.integers(0, 9, (h, w)).astype(np.uint32) << 16)
+        for seg in (seg_all, seg_mixed):
+            for pc in (oracle_py.fxaa_push(w, h), oracle_py.fxaa_push(w, h, subpix=0.25, edge_threshold=0.333, edge_threshold_min=0.0312),
+                       oracle_py.fxaa_push(w, h, subpix=1.0, edge_threshold=0.063, edge_threshold_min=0.0)):
+                for gather4 in (True, False):
+                    a = oracle_py.fxaa(prep, seg, pc, gather4=gather4)
+                    b = oracle_py.fxaa(prep, seg, pc, gather4=gather4, impl="ref")
+                    assert mismatch_report(f"fxaa {h}x{w} gather4={gather4}", b, a) is None
+        # FXAA must actually do something on this image, and the two texel-access variants must not be the same code path
+        out = oracle_py.fxaa(prep, seg_all, oracle_py.fxaa_push(w, h))
+        if h > 8:
+            assert (bits16(out) != bits16(prep)).any()
