@@ -42,5 +42,6 @@ for r in rows:
 tot = sum(lines.values())
 tot_s = sum(stalls.values()) or 1
 print(f"kernel filter '{want}': {tot / (px / 32):.1f} warp instructions per pixel-thread in total")
-for key, n in sorted(lines.items(), key=lambda kv: -kv[1])[:topn]:
+order = (lambda kv: -stalls[kv[0]]) if len(sys.argv) > 5 and sys.argv[5] == "stalls" else (lambda kv: -kv[1])
+for key, n in sorted(lines.items(), key=order)[:topn]:
     print(f"{n / (px / 32):7.1f}  {100.0 * stalls[key] / tot_s:5.1f}%  {key[0]}:{key[1]:<4d} {key[2]}")

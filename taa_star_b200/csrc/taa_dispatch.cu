@@ -1,6 +1,7 @@
 // taa_dispatch.cu — chooses the resolve kernel for a settings block (every switch of
 // `Parameters` is uniform across a dispatch except the split-screen select).
 #include "taa_ctx.h"
+#include <cstdlib>
 
 namespace taa {
 
@@ -23,7 +24,10 @@ cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, i
 		unsigned int* cnt = c->fix_count + c->fix_parity;
 		unsigned int* cnt_next = c->fix_count + (c->fix_parity ^ 1);
 		c->fix_parity ^= 1;
-		e = launch_resolve_tuned(A, c->fix_list, cnt, cnt_next, (c->desc.flags & TAA_FLAG_FIXUP_ALL) != 0, s);
+		// TAA_TUNED_VARIANT=tile selects the 32x32-tile kernel (A/B aid); both honour the same contract
+		static const bool tile = [] { const char* v = getenv("TAA_TUNED_VARIANT"); return v && v[0] == 't'; }();
+		e = tile ? launch_resolve_tuned(A, c->fix_list, cnt, cnt_next, (c->desc.flags & TAA_FLAG_FIXUP_ALL) != 0, s)
+		         : launch_resolve_strip(A, c->fix_list, cnt, cnt_next, (c->desc.flags & TAA_FLAG_FIXUP_ALL) != 0, s);
 		if (e != cudaSuccess) return e;
 		*launched = 1;
 		e = launch_resolve_fixup(A, c->fix_list, cnt, A.result.p != nullptr, c->num_sms, s);

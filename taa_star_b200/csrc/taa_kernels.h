@@ -16,6 +16,9 @@ cudaError_t launch_resolve_fixup(const ResolveArgs& args, const unsigned int* li
 bool tuned_supports(const ResolveArgs& args);
 cudaError_t launch_resolve_tuned(const ResolveArgs& args, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next,
                                  bool fixup_all, cudaStream_t stream);
+// the same contract with long column strips and a history window that runs one row ahead (taa_resolve_strip.cu): the default
+cudaError_t launch_resolve_strip(const ResolveArgs& args, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next,
+                                 bool fixup_all, cudaStream_t stream);
 
 // follow-on passes, one kernel each as the reference dispatches them (taa_post.cu)
 struct PostImg { Img src; Img debug; ImgW dst; int w, h; };
