@@ -99,12 +99,22 @@ __device__ __forceinline__ void stage_tile(const Img& im, uint2 (*dst)[RW], int 
 	const bool fast = x0 >= 2 && x0 + TW + 1 <= W - 1 && (((unsigned long long)im.p | (unsigned long long)im.pitch) & 15ull) == 0ull;  // CTA-uniform
 	if (fast) {
 		const unsigned char* base = im.p + ((size_t)(x0 - 2) * 8u + (size_t)lane * 16u);
-		for (int r = warp; r < nrow; r += NWARP) {
-			const int ly = iclamp(iclamp(gy0 + r, 0, H - 1) - im.y0, 0, im.rows - 1);
-			const unsigned char* src = base + (size_t)ly * (size_t)im.pitch;
-			unsigned char* d = reinterpret_cast<unsigned char*>(&dst[r][0]) + lane * 16;
-			cp_async16(d, src);
-			if (lane < RW / 2 - 32) cp_async16(d + 512, src + 512);
+		unsigned char* d = reinterpret_cast<unsigned char*>(&dst[warp][0]) + lane * 16;
+		const int lo = max(0, im.y0), hi = min(H - 1, im.y0 + im.rows - 1);
+		if (gy0 >= lo && gy0 + nrow - 1 <= hi) {  // no row is clamped: walk the pointer
+			const unsigned char* src = base + (size_t)(gy0 + warp - im.y0) * (size_t)im.pitch;
+			const size_t step = (size_t)NWARP * (size_t)im.pitch;
+			for (int r = warp; r < nrow; r += NWARP, src += step, d += NWARP * RROW) {
+				cp_async16(d, src);
+				if (lane < RW / 2 - 32) cp_async16(d + 512, src + 512);
+			}
+		} else {
+			for (int r = warp; r < nrow; r += NWARP, d += NWARP * RROW) {
+				const int ly = iclamp(iclamp(gy0 + r, 0, H - 1) - im.y0, 0, im.rows - 1);
+				const unsigned char* src = base + (size_t)ly * (size_t)im.pitch;
+				cp_async16(d, src);
+				if (lane < RW / 2 - 32) cp_async16(d + 512, src + 512);
+			}
 		}
 	} else {
 		const int c0 = iclamp(x0 - 2 + lane, 0, W - 1), c1 = iclamp(x0 + 30 + lane, 0, W - 1), c2 = iclamp(x0 + 62 + lane, 0, W - 1);
@@ -122,7 +132,7 @@ __device__ __forceinline__ void stage_tile(const Img& im, uint2 (*dst)[RW], int 
 // FAST = the tile's motion is uniform (every staged velocity texel bit-identical, no mover near, all footprints interior, footprint
 // rows advancing one per pixel row): history coordinates and Catmull-Rom weights come from the per-row / per-column tables, and the
 // window never restarts. The arithmetic is the very same as in the general path (same functions of the same inputs).
-template <bool REJ, bool ALPHA, bool FAST>
+template <bool REJ, bool ALPHA, bool FAST, int UNR>
 __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
                                              const float fix_band, const int x0, const int y0, const int rows_valid, const int warp, const int lane) {
 	const TaaParameters& P = A.ubo.param[0];
@@ -220,7 +230,7 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 		hoff += 4u * hpitch;
 	}
 
-#pragma unroll 4
+#pragma unroll UNR
 	for (int rr = 0; rr < nr; ++rr) {
 		const int rt = r0 + rr;  // tile row of this pixel
 
@@ -239,7 +249,7 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 			hu = f_hu; hv = rw.h; velz = f_velz;
 			ayw0 = rw.w[0]; ayw1 = rw.w[1]; ayw2 = rw.w[2]; ayw3 = rw.w[3];
 			f_ty = rw.tc; f_outy = rw.outside != 0u;
-			ahead = REJ || rr + 1 < nr;
+			ahead = true;  // (the row after the strip's last footprint is requested too: it is in the buffer, see the vote)
 		} else {
 			// ---- getHistoryPosition (taa.comp:391-438), exact ----
 			const VelT vr = sm.vrow[rt];
@@ -342,7 +352,12 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 				e1 = __ldg(reinterpret_cast<const unsigned int*>(p + 36));
 			}
 		}
-		if (FAST) hoff += hpitch;
+		if (FAST) {
+			hoff += hpitch;
+			// hint for the row the NEXT iteration requests: even lanes touch the first, odd lanes the last texel of their four, which
+			// together cover every 32-byte sector of the warp's row segment
+			asm volatile("prefetch.global.L1 [%0];" ::"l"(hbase + (hoff + ((lane & 1) ? 24u : 0u))));
+		}
 
 		const float3 cur = cur_next;
 		float3 s1c, s2c;
@@ -501,7 +516,7 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 	}
 }
 
-template <bool REJ, bool ALPHA, int MINB>
+template <bool REJ, bool ALPHA, int MINB, int UNR>
 __global__ void __launch_bounds__(NT, MINB)
 taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
                          unsigned int* __restrict__ fix_count_next, const float fix_band) {
@@ -574,6 +589,25 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 	asm volatile("cp.async.wait_group 0;" ::: "memory");
 	__syncthreads();
 
+	// ---- warm L1 with the history rows the strips start from (the window of a strip's first pixel is the one gather nothing hides) ----
+	// A hint only: the position is guessed from the tile's first velocity texel.
+	{
+		const float2 vg = __half22float2(h2(sm.vraw[0][0].x));
+		const int wx = warp & 1, wy = warp >> 1;
+		const int r0 = min(wy * RPT, max(rows_valid - 1, 0));
+		const float hu = sm.vcol[wx * 32 + lane].c - vg.x, hv = sm.vrow[r0].c - vg.y;
+		const int kx = (int)fminf(fmaxf(floorf(hu * fW - 0.5f) - 1.0f, 0.0f), fW - 4.0f);
+		const int ky = (int)fminf(fmaxf(floorf(hv * fH - 0.5f) - 1.0f, 0.0f), fH - 1.0f);
+		const int rlo = max(0, A.history_in.y0), rhi = min(H - 1, A.history_in.y0 + A.history_in.rows - 1);
+#pragma unroll
+		for (int i = 0; i < 5; ++i) {
+			const int gy = iclamp(ky + i, rlo, rhi);
+			const unsigned char* p = A.history_in.p + (size_t)(gy - A.history_in.y0) * (size_t)A.history_in.pitch + (size_t)kx * 8u;
+			asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+			asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 24));
+		}
+	}
+
 	// ---- is the tile's motion uniform? (vote, taken at the barrier inside phase 1) -------------------
 	// Every staged velocity texel bit-identical and finite, no mover within two texels of the tile, every history footprint of the
 	// tile interior to the image / band buffer, footprint rows advancing by exactly one per pixel row.
@@ -605,7 +639,7 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 				const AxisW a = catmull_axis(hv, fH, invh);
 				t.w[0] = a.w[0]; t.w[1] = a.w[1]; t.w[2] = a.w[2]; t.w[3] = a.w[3];
 				t.k = a.k; t.tc = (int)(hv * fH); t.outside = (hv < 0.f || hv >= 1.f) ? 1u : 0u; t.h = hv;
-				vote = vote && a.k - 1 - ring >= hlo && a.k + 2 + ring <= hhi;
+				vote = vote && a.k - 1 - ring >= hlo && a.k + 3 <= hhi;  // (row k + 3 is the look-ahead row of the window)
 				if (r + 1 < rows_valid) vote = vote && catmull_axis(sm.vrow[r + 1].c - vxy.y, fH, invh).k == a.k + 1;
 				sm.roww[r] = t;
 			}
@@ -625,7 +659,8 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		float3 va[NR], vb[NR], ve = make_float3(0.f, 0.f, 0.f);
 #pragma unroll
 		for (int k = 0; k < NR; ++k) {
-			const int r = min(warp + k * NWARP, nrows - 1);
+			const int r = warp + k * NWARP;
+			if (r >= nrows) break;  // warp-uniform
 			const ColT cy = sm.crow[r];
 			const __half py = __float2half_rn(cy.p);
 			va[k] = sample_ycocg(*reinterpret_cast<const uint2*>(cr + (cy.m + ca.m)), *reinterpret_cast<const uint2*>(cr + (cy.m + ca.n)),
@@ -653,13 +688,13 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 	}
 	__syncthreads();
 
-	if (fast) strip_phase2<REJ, ALPHA, true>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane);
-	else strip_phase2<REJ, ALPHA, false>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane);
+	if (fast) strip_phase2<REJ, ALPHA, true, UNR>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane);
+	else strip_phase2<REJ, ALPHA, false, UNR>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane);
 }
 
-template <bool REJ, bool ALPHA, int MINB>
+template <bool REJ, bool ALPHA, int MINB, int UNR>
 cudaError_t launch_variant(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, float band, cudaStream_t stream) {
-	auto kern = taa_resolve_strip_kernel<REJ, ALPHA, MINB>;
+	auto kern = taa_resolve_strip_kernel<REJ, ALPHA, MINB, UNR>;
 	static bool configured = false;  // per variant
 	if (!configured) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StripSmem));
@@ -671,15 +706,15 @@ cudaError_t launch_variant(const ResolveArgs& A, unsigned int* fix_list, unsigne
 	return cudaGetLastError();
 }
 
-template <int MINB>
+template <int MINB, int UNR>
 cudaError_t launch_minb(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, float band, cudaStream_t stream) {
 	const TaaParameters& P = A.ubo.param[0];
 	const bool rej = P.mDepthCulling || P.mRejectOutside || P.mDynamicAntiGhosting;
 	const bool alp = P.mVelBasedAlpha || P.mLumaWeightingLottes || P.mReduceBlendNearClamp;
-	if (rej) return alp ? launch_variant<true, true, MINB>(A, fix_list, fix_count, fix_count_next, band, stream)
-	                    : launch_variant<true, false, MINB>(A, fix_list, fix_count, fix_count_next, band, stream);
-	return alp ? launch_variant<false, true, MINB>(A, fix_list, fix_count, fix_count_next, band, stream)
-	           : launch_variant<false, false, MINB>(A, fix_list, fix_count, fix_count_next, band, stream);
+	if (rej) return alp ? launch_variant<true, true, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream)
+	                    : launch_variant<true, false, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream);
+	return alp ? launch_variant<false, true, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream)
+	           : launch_variant<false, false, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream);
 }
 
 }  // namespace
@@ -687,9 +722,19 @@ cudaError_t launch_minb(const ResolveArgs& A, unsigned int* fix_list, unsigned i
 cudaError_t launch_resolve_strip(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, bool fixup_all,
                                  cudaStream_t stream) {
 	const float band = fixup_all ? INFINITY : FIXUP_BAND_4K * fmaxf(1.0f, fmaxf((float)A.out_w / 3840.0f, (float)A.out_h / 3840.0f));
-	static const int minb = [] { const char* s = getenv("TAA_STRIP_MINB"); return s ? atoi(s) : 3; }();  // tuning aid
-	return minb == 2 ? launch_minb<2>(A, fix_list, fix_count, fix_count_next, band, stream)
-	                 : launch_minb<3>(A, fix_list, fix_count, fix_count_next, band, stream);
+	// Defaults from the A/B on B200 (scripts/strip_ab.sh): the strip loop not unrolled (no spills at the 80-register cap); three CTAs/SM
+	// for the plain variants, two (128 registers) for the rejection variants, whose window state does not fit 80 registers.
+	const TaaParameters& P = A.ubo.param[0];
+	const bool rej = P.mDepthCulling || P.mRejectOutside || P.mDynamicAntiGhosting;
+	static const int minb_env = [] { const char* s = getenv("TAA_STRIP_MINB"); return s ? atoi(s) : 0; }();  // tuning aids
+	static const int unr = [] { const char* s = getenv("TAA_STRIP_UNROLL"); return s ? atoi(s) : 1; }();
+	const int minb = minb_env ? minb_env : (rej ? 2 : 3);
+#define TAA_STRIP_GO(MB, UN) return launch_minb<MB, UN>(A, fix_list, fix_count, fix_count_next, band, stream)
+	if (minb == 2) { if (unr == 1) TAA_STRIP_GO(2, 1); if (unr == 2) TAA_STRIP_GO(2, 2); TAA_STRIP_GO(2, 4); }
+	if (unr == 1) TAA_STRIP_GO(3, 1);
+	if (unr == 2) TAA_STRIP_GO(3, 2);
+	TAA_STRIP_GO(3, 4);
+#undef TAA_STRIP_GO
 }
 
 }  // namespace taa
