@@ -637,6 +637,9 @@ __device__ __forceinline__ void resolve_pixel_exact_family(const ResolveArgs& A,
 template <bool WRITE_SCREEN>
 __global__ void __launch_bounds__(128) taa_resolve_fixup_kernel(const __grid_constant__ ResolveArgs A, const unsigned int* __restrict__ list,
                                                                 const unsigned int* __restrict__ count) {
+	// launched with programmatic stream serialisation right behind the tuned kernel: set-up overlaps that kernel's tail, and
+	// nothing it wrote (list, count, images) is read before it has completed and flushed
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 	const unsigned int n = *count;
 	for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const unsigned int p = list[i];
@@ -654,10 +657,18 @@ cudaError_t launch_resolve_generic(const ResolveArgs& args, cudaStream_t stream)
 
 cudaError_t launch_resolve_fixup(const ResolveArgs& args, const unsigned int* list, const unsigned int* count, bool write_screen, int num_sms,
                                  cudaStream_t stream) {
-	const int grid = num_sms * 8;  // the count lives on the device: surplus CTAs find nothing to do and exit
-	if (write_screen) taa_resolve_fixup_kernel<true><<<grid, 128, 0, stream>>>(args, list, count);
-	else taa_resolve_fixup_kernel<false><<<grid, 128, 0, stream>>>(args, list, count);
-	return cudaGetLastError();
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(num_sms * 8);  // the count lives on the device: surplus CTAs find nothing to do and exit
+	cfg.blockDim = dim3(128);
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	if (write_screen) return cudaLaunchKernelEx(&cfg, taa_resolve_fixup_kernel<true>, args, list, count);
+	return cudaLaunchKernelEx(&cfg, taa_resolve_fixup_kernel<false>, args, list, count);
 }
 
 }  // namespace taa

@@ -58,6 +58,7 @@ struct __align__(16) StripSmem {
 	AxisT colw[TW];
 	ColT crow[SH];
 	ColT ccol[SW];
+	unsigned long long mbar;              // completion barrier of the bulk copies that stage the raw tiles
 	unsigned long long wmask[2][TH + 4];  // [half][r], bit c: velocity.w != 0 at texel (x0 + 32 half - 2 + c, y0 - 2 + r), clamped to the image
 };
 static_assert(sizeof(StripSmem) <= 75 * 1024, "three CTAs per SM");
@@ -90,6 +91,39 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned int)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+// ---- bulk (TMA) staging: one thread copies one whole tile row (544 bytes) global -> shared, completion counted on an mbarrier ----
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_row(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+	             "r"(smem_u32(bar)) : "memory");
+}
+// source row of tile row r (rows gy0 ..): clamped to the image, then silently into the rows the buffer holds
+__device__ __forceinline__ const unsigned char* tile_src_row(const Img& im, int gy, int x0, int H) {
+	const int ly = iclamp(iclamp(gy, 0, H - 1) - im.y0, 0, im.rows - 1);
+	return im.p + (size_t)ly * (size_t)im.pitch + (size_t)(x0 - 2) * 8u;
+}
+__device__ __forceinline__ bool bulk_ok(const Img& im, int x0, int W) {  // CTA-uniform: no column is clamped, 16-byte aligned rows
+	return x0 >= 2 && x0 + TW + 1 <= W - 1 && (((unsigned long long)im.p | (unsigned long long)im.pitch) & 15ull) == 0ull;
 }
 
 // Stage rows gy0 .. gy0 + nrow - 1 (clamped to the image, then silently into the rows the buffer holds: the tables of phase 0 report
@@ -519,7 +553,7 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 template <bool REJ, bool ALPHA, int MINB, int UNR>
 __global__ void __launch_bounds__(NT, MINB)
 taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
-                         unsigned int* __restrict__ fix_count_next, const float fix_band) {
+                         unsigned int* __restrict__ fix_count_next, const float fix_band, const bool use_bulk) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	StripSmem& sm = *reinterpret_cast<StripSmem*>(smem_raw);
 	const TaaParameters& P = A.ubo.param[0];
@@ -535,9 +569,28 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 	if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && fix_count_next) *fix_count_next = 0u;  // the counter the next frame appends to
 
 	// ---- stage the raw tiles: everything the CTA touches for the first time is requested here, at once ----
-	stage_tile(A.color, sm.u.craw, y0 - 2, rows_valid + 4, x0, W, H, warp, lane);
-	stage_tile(A.velocity, sm.vraw, y0 - 1, rows_valid + 2, x0, W, H, warp, lane);
-	asm volatile("cp.async.commit_group;" ::: "memory");
+	// Default: per-thread cp.async (16 bytes per lane and row). use_bulk (TAA_STRIP_BULK=1): warp 0 issues one bulk (TMA) copy per tile row
+	// (70 copies of 544 bytes) on interior tiles instead — measured SLOWER on B200 (0.145 vs 0.137 ms per 4K frame: the CTA then sits a
+	// quarter of its stall samples at the mbarrier), so it stays an A/B knob.
+	const bool bulk = use_bulk && bulk_ok(A.color, x0, W) && bulk_ok(A.velocity, x0, W);
+	if (bulk) {
+		if (warp == 0) {
+			const int nc = rows_valid + 4, nv = rows_valid + 2;
+			if (lane == 0) {
+				mbar_init(&sm.mbar, 1u);
+				mbar_expect_tx(&sm.mbar, (unsigned int)(nc + nv) * RROW);
+			}
+			__syncwarp();
+			for (int r = lane; r < nc + nv; r += 32) {
+				if (r < nc) bulk_row(&sm.u.craw[r][0], tile_src_row(A.color, y0 - 2 + r, x0, H), RROW, &sm.mbar);
+				else bulk_row(&sm.vraw[r - nc][0], tile_src_row(A.velocity, y0 - 1 + (r - nc), x0, H), RROW, &sm.mbar);
+			}
+		}
+	} else {
+		stage_tile(A.color, sm.u.craw, y0 - 2, rows_valid + 4, x0, W, H, warp, lane);
+		stage_tile(A.velocity, sm.vraw, y0 - 1, rows_valid + 2, x0, W, H, warp, lane);
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	}
 
 	// ---- phase 0: coordinate tables (while the tiles arrive) ---------------------------------------
 	for (int i = tid; i < SW + (rows_valid + 2) + TW + rows_valid; i += NT) {
@@ -586,8 +639,9 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 			}
 		}
 	}
-	asm volatile("cp.async.wait_group 0;" ::: "memory");
-	__syncthreads();
+	if (!bulk) asm volatile("cp.async.wait_group 0;" ::: "memory");
+	__syncthreads();  // tables, (mbarrier initialised,) cp.async data of all threads
+	if (bulk) mbar_wait(&sm.mbar, 0u);
 
 	// ---- warm L1 with the history rows the strips start from (the window of a strip's first pixel is the one gather nothing hides) ----
 	// A hint only: the position is guessed from the tile's first velocity texel.
@@ -702,7 +756,8 @@ cudaError_t launch_variant(const ResolveArgs& A, unsigned int* fix_list, unsigne
 		configured = true;
 	}
 	dim3 grid((A.out_w + TW - 1) / TW, (A.band_rows + TH - 1) / TH);
-	kern<<<grid, NT, sizeof(StripSmem), stream>>>(A, fix_list, fix_count, fix_count_next, band);
+	static const bool use_bulk = [] { const char* v = getenv("TAA_STRIP_BULK"); return v && v[0] == '1'; }();
+	kern<<<grid, NT, sizeof(StripSmem), stream>>>(A, fix_list, fix_count, fix_count_next, band, use_bulk);
 	return cudaGetLastError();
 }
 
