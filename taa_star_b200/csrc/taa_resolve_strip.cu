@@ -566,6 +566,7 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 	const float fW = (float)W, fH = (float)H;
 	const float invw = 1.0f / fW, invh = 1.0f / fH;
 
+	asm volatile("griddepcontrol.wait;" ::: "memory");  // see launch_variant
 	if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && fix_count_next) *fix_count_next = 0u;  // the counter the next frame appends to
 
 	// ---- stage the raw tiles: everything the CTA touches for the first time is requested here, at once ----
@@ -757,8 +758,19 @@ cudaError_t launch_variant(const ResolveArgs& A, unsigned int* fix_list, unsigne
 	}
 	dim3 grid((A.out_w + TW - 1) / TW, (A.band_rows + TH - 1) / TH);
 	static const bool use_bulk = [] { const char* v = getenv("TAA_STRIP_BULK"); return v && v[0] == '1'; }();
-	kern<<<grid, NT, sizeof(StripSmem), stream>>>(A, fix_list, fix_count, fix_count_next, band, use_bulk);
-	return cudaGetLastError();
+	// programmatic stream serialisation: the launch set-up overlaps the tail of whatever kernel precedes it in the stream (normally the
+	// previous frame's fix-up pass); the kernel itself waits for that kernel's completion before it touches memory
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = dim3(NT);
+	cfg.dynamicSmemBytes = sizeof(StripSmem);
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kern, A, fix_list, fix_count, fix_count_next, band, use_bulk);
 }
 
 template <int MINB, int UNR>
