@@ -37,7 +37,7 @@ constexpr int NT = 32 * NWARP;
 constexpr int SW = TW + 2, SH = TH + 2;  // sampled-colour tile: 1-texel halo
 constexpr int RW = TW + 4;               // raw tiles: columns x0 - 2 .. x0 + 65 (16-byte aligned rows)
 constexpr int CRH = TH + 4;              // raw colour rows y0 - 2 .. y0 + 33
-constexpr int VRH = TH + 2;              // raw velocity rows y0 - 1 .. y0 + 32
+constexpr int VRH = TH + 4;              // raw velocity rows y0 - 2 .. y0 + 33 (the mover mask looks two texels out)
 constexpr unsigned int RROW = RW * 8u;   // bytes per raw tile row
 
 struct ColT { unsigned int m, n; float p; };                          // colour tap along one axis: byte offsets of the main texel and of its bleeding neighbour in the raw tile, weight
@@ -52,6 +52,7 @@ struct __align__(16) StripSmem {
 		uint2 craw[CRH][RW];   // raw colour texels (cp.async target, phase 1 input)
 	} u;
 	uint2 vraw[VRH][RW];
+	float dtile[TH][TW];   // current depth of the tile's pixels (rejection variants with depth culling)
 	VelT vrow[TH];
 	VelT vcol[TW];
 	AxisT roww[TH];
@@ -192,8 +193,7 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 	unsigned int o_hist = (unsigned int)(y0 + r0 - A.history_out.y0) * (unsigned int)A.history_out.pitch + (unsigned int)xs * 8u;
 	unsigned int o_res = (unsigned int)(y0 + r0 - A.result.y0) * (unsigned int)A.result.pitch + (unsigned int)xs * 8u;
 	unsigned int o_mask = (unsigned int)(y0 + r0 - A.mask.y0) * (unsigned int)A.mask.pitch + (unsigned int)xs * 4u;
-	unsigned int o_depth = 0u;
-	if (REJ) o_depth = row_off(A.depth, y0 + r0, st) + (unsigned int)xs * 4u;
+	if (REJ && P.mDepthCulling) { row_off(A.depth, y0 + r0, st); row_off(A.depth, y0 + r0 + nr - 1, st); }  // reports rows a band buffer does not hold
 
 	const float gg = P.mVarClipGamma * P.mVarClipGamma, gg9 = gg * (1.0f / 9.0f);
 	// row sums of the first two neighbourhood rows of the strip
@@ -227,6 +227,7 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 	float f_hu = 0.f, f_velz = 0.f;
 	int f_tx = 0;
 	bool f_outx = false;
+	float f_hd = 0.f;        // previous depth at the history position of the pixel (requested one pixel ahead)
 	unsigned int hoff = 0u;  // byte offset of the row in flight (first tap column) in the history buffer
 	if (FAST) {
 		const AxisT cw = sm.colw[lx];
@@ -262,14 +263,15 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 		hr2 = hfilter<REJ>(q[8], q[9], q[10], q[11], axs.w);
 		hr3 = hfilter<REJ>(q[12], q[13], q[14], q[15], axs.w);
 		hoff += 4u * hpitch;
+		if (REJ && P.mDepthCulling) f_hd = fetch_r32f(A.history_depth, W, H, f_tx, sm.roww[r0].tc, st);
 	}
 
 #pragma unroll UNR
 	for (int rr = 0; rr < nr; ++rr) {
 		const int rt = r0 + rr;  // tile row of this pixel
 
-		float depth = 0.f;
-		if (REJ && P.mDepthCulling) depth = __ldg(reinterpret_cast<const float*>(A.depth.p + o_depth));  // used after the history filter
+		float depth = 0.f, f_hd_next = 0.f;
+		if (REJ && P.mDepthCulling) depth = sm.dtile[rt][lx];
 		float v, hu, hv, velz = 0.f;
 		float ayw0, ayw1, ayw2, ayw3;
 		int K = 0, f_ty = 0;
@@ -284,6 +286,7 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 			ayw0 = rw.w[0]; ayw1 = rw.w[1]; ayw2 = rw.w[2]; ayw3 = rw.w[3];
 			f_ty = rw.tc; f_outy = rw.outside != 0u;
 			ahead = true;  // (the row after the strip's last footprint is requested too: it is in the buffer, see the vote)
+			if (REJ && P.mDepthCulling && rr + 1 < nr) f_hd_next = fetch_r32f(A.history_depth, W, H, f_tx, sm.roww[rt + 1].tc, st);
 		} else {
 			// ---- getHistoryPosition (taa.comp:391-438), exact ----
 			const VelT vr = sm.vrow[rt];
@@ -455,10 +458,9 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 			if (P.mDepthCulling) {
 				const float expected = depth - velz;
 				const int tx = FAST ? f_tx : (int)(hu * fW), ty = FAST ? f_ty : (int)(hv * fH);
-				const float hd = fetch_r32f(A.history_depth, W, H, tx, ty, st);
+				const float hd = FAST ? f_hd : fetch_r32f(A.history_depth, W, H, tx, ty, st);
 				if (fabsf(hd - expected) > 0.1f * (1.0f - hd)) rejected = true;
 			}
-			o_depth += (unsigned int)A.depth.pitch;
 		}
 
 		// ---- clipAabb towards the box centre (taa.comp:323-345) ----
@@ -525,6 +527,8 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 		if (!FAST) {
 			sh_K = K + 1;
 			sh_valid = ahead;
+		} else {
+			f_hd = f_hd_next;
 		}
 		if (uncertain && xvalid) fixbits |= 1u << rr;
 	}
@@ -546,6 +550,21 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 			const int b = __ffs(fixbits) - 1;
 			fixbits &= fixbits - 1u;
 			fix_list[slot++] = (unsigned int)(y0 + r0 + b) * (unsigned int)W + (unsigned int)x;
+		}
+	}
+}
+
+// Stage the tile's own depth texels (4 bytes each): rows y0 .. y0 + nrow - 1, columns x0 .. x0 + 63.
+__device__ __forceinline__ void stage_depth(const Img& im, float (*dst)[TW], int y0, int nrow, int x0, int W, int warp, int lane) {
+	const bool fast = x0 + TW <= W && (((unsigned long long)im.p | (unsigned long long)im.pitch) & 15ull) == 0ull;  // CTA-uniform
+	for (int r = warp; r < nrow; r += NWARP) {
+		const int ly = iclamp(y0 + r - im.y0, 0, im.rows - 1);
+		const unsigned char* src = im.p + (size_t)ly * (size_t)im.pitch;
+		if (fast) {
+			if (lane < TW / 4) cp_async16(&dst[r][4 * lane], src + (size_t)x0 * 4u + (size_t)lane * 16u);
+		} else {
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&dst[r][lane])), "l"(src + (size_t)min(x0 + lane, W - 1) * 4u) : "memory");
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&dst[r][lane + 32])), "l"(src + (size_t)min(x0 + lane + 32, W - 1) * 4u) : "memory");
 		}
 	}
 }
@@ -576,7 +595,7 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 	const bool bulk = use_bulk && bulk_ok(A.color, x0, W) && bulk_ok(A.velocity, x0, W);
 	if (bulk) {
 		if (warp == 0) {
-			const int nc = rows_valid + 4, nv = rows_valid + 2;
+			const int nc = rows_valid + 4, nv = rows_valid + 4;
 			if (lane == 0) {
 				mbar_init(&sm.mbar, 1u);
 				mbar_expect_tx(&sm.mbar, (unsigned int)(nc + nv) * RROW);
@@ -584,12 +603,17 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 			__syncwarp();
 			for (int r = lane; r < nc + nv; r += 32) {
 				if (r < nc) bulk_row(&sm.u.craw[r][0], tile_src_row(A.color, y0 - 2 + r, x0, H), RROW, &sm.mbar);
-				else bulk_row(&sm.vraw[r - nc][0], tile_src_row(A.velocity, y0 - 1 + (r - nc), x0, H), RROW, &sm.mbar);
+				else bulk_row(&sm.vraw[r - nc][0], tile_src_row(A.velocity, y0 - 2 + (r - nc), x0, H), RROW, &sm.mbar);
 			}
+		}
+		if (REJ && P.mDepthCulling) {
+			stage_depth(A.depth, sm.dtile, y0, rows_valid, x0, W, warp, lane);
+			asm volatile("cp.async.commit_group;" ::: "memory");
 		}
 	} else {
 		stage_tile(A.color, sm.u.craw, y0 - 2, rows_valid + 4, x0, W, H, warp, lane);
-		stage_tile(A.velocity, sm.vraw, y0 - 1, rows_valid + 2, x0, W, H, warp, lane);
+		stage_tile(A.velocity, sm.vraw, y0 - 2, rows_valid + 4, x0, W, H, warp, lane);
+		if (REJ && P.mDepthCulling) stage_depth(A.depth, sm.dtile, y0, rows_valid, x0, W, warp, lane);
 		asm volatile("cp.async.commit_group;" ::: "memory");
 	}
 
@@ -621,26 +645,11 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 			const float v = ((float)y + 0.5f) / fH;
 			Lin L = lin_coord(v, H);
 			row_off(A.velocity, L.i0, st); row_off(A.velocity, L.i1, st);
-			VelT t = {(unsigned int)(iclamp(L.i0 - (y0 - 1), 0, VRH - 1)) * RROW, (unsigned int)(iclamp(L.i1 - (y0 - 1), 0, VRH - 1)) * RROW, L.a, v};
+			VelT t = {(unsigned int)(iclamp(L.i0 - (y0 - 2), 0, VRH - 1)) * RROW, (unsigned int)(iclamp(L.i1 - (y0 - 2), 0, VRH - 1)) * RROW, L.a, v};
 			sm.vrow[j] = t;
 		}
 	}
-	// Movers (velocity.w != 0, fwd_geometry.frag:289-295) are what the 5-tap anti-ghosting test looks for (taa.comp:796-811). Every tap's
-	// bilinear footprint lies inside the 5x5 texels around the pixel; where all of them have w == +-0 the taps return w == 0 exactly.
-	if (REJ && P.mDynamicAntiGhosting) {
-		for (int r = warp; r < rows_valid + 4; r += NWARP) {
-			const uint2* vp = reinterpret_cast<const uint2*>(A.velocity.p + (size_t)row_off(A.velocity, iclamp(y0 - 2 + r, 0, H - 1), st));
-			const unsigned int wa = __ldg(vp + iclamp(x0 - 2 + lane, 0, W - 1)).y & 0x7fff0000u;
-			const unsigned int wb = __ldg(vp + iclamp(x0 + 30 + lane, 0, W - 1)).y & 0x7fff0000u;
-			const unsigned int wc = lane < 4 ? (__ldg(vp + iclamp(x0 + 62 + lane, 0, W - 1)).y & 0x7fff0000u) : 0u;
-			const unsigned int b0 = __ballot_sync(0xffffffffu, wa != 0u), b1 = __ballot_sync(0xffffffffu, wb != 0u), b2 = __ballot_sync(0xffffffffu, wc != 0u);
-			if (lane == 0) {
-				sm.wmask[0][r] = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
-				sm.wmask[1][r] = (unsigned long long)b1 | ((unsigned long long)b2 << 32);
-			}
-		}
-	}
-	if (!bulk) asm volatile("cp.async.wait_group 0;" ::: "memory");
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
 	__syncthreads();  // tables, (mbarrier initialised,) cp.async data of all threads
 	if (bulk) mbar_wait(&sm.mbar, 0u);
 
@@ -670,12 +679,12 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 	{
 		const uint2 vref = sm.vraw[0][0];
 		const uint4* vr4 = reinterpret_cast<const uint4*>(&sm.vraw[0][0]);
-		for (int i = tid; i < (rows_valid + 2) * (RW / 2); i += NT) {
+		for (int i = tid; i < (rows_valid + 4) * (RW / 2); i += NT) {
 			const uint4 t = vr4[i];
 			vote = vote && t.x == vref.x && t.z == vref.x && (!REJ || (t.y == vref.y && t.w == vref.y));
 		}
 		vote = vote && finite2(vref.x) && (!REJ || finite2(vref.y));
-		if (REJ && P.mDynamicAntiGhosting && tid < 2 * (rows_valid + 4)) vote = vote && sm.wmask[tid & 1][tid >> 1] == 0ull;
+		if (REJ && P.mDynamicAntiGhosting) vote = vote && (vref.y & 0x7fff0000u) == 0u;  // no mover within two texels of the tile
 		const int hlo = max(0, A.history_in.y0), hhi = min(H - 1, A.history_in.y0 + A.history_in.rows - 1);
 		const int ring = REJ ? 1 : 0;
 		if (tid < TW + rows_valid) {
@@ -731,6 +740,21 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 			                  *reinterpret_cast<const uint2*>(cr + (cy.n + cx.m)), __float2half_rn(cx.p), __float2half_rn(cy.p));
 		}
 		fast = __syncthreads_and(vote ? 1 : 0) != 0;
+		// Movers (velocity.w != 0, fwd_geometry.frag:289-295) are what the 5-tap anti-ghosting test looks for (taa.comp:796-811). Every tap's
+		// bilinear footprint lies inside the 5x5 texels around the pixel; where all of them have w == +-0 the taps return w == 0 exactly.
+		// Only the general path needs the mask (a uniform tile has none); it is read after the next barrier.
+		if (REJ && !fast && P.mDynamicAntiGhosting) {
+			for (int r = warp; r < rows_valid + 4; r += NWARP) {
+				row_off(A.velocity, iclamp(y0 - 2 + r, 0, H - 1), st);  // reports rows a band buffer does not hold
+				const unsigned int wa = sm.vraw[r][lane].y & 0x7fff0000u, wb = sm.vraw[r][lane + 32].y & 0x7fff0000u;
+				const unsigned int wc = lane < 4 ? (sm.vraw[r][lane + 64].y & 0x7fff0000u) : 0u;
+				const unsigned int b0 = __ballot_sync(0xffffffffu, wa != 0u), b1 = __ballot_sync(0xffffffffu, wb != 0u), b2 = __ballot_sync(0xffffffffu, wc != 0u);
+				if (lane == 0) {
+					sm.wmask[0][r] = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
+					sm.wmask[1][r] = (unsigned long long)b1 | ((unsigned long long)b2 << 32);
+				}
+			}
+		}
 #pragma unroll
 		for (int k = 0; k < NR; ++k) {
 			const int r = warp + k * NWARP;
