@@ -46,23 +46,25 @@ struct __align__(16) VelT { unsigned int o0, o1; float a, c; };       // velocit
 // Uniform-motion tiles: Catmull-Rom weights per tile row / tile column (the history position is separable then)
 struct __align__(16) AxisT { float w[4]; int k; int tc; unsigned int outside; float h; };  // weights, first-tap texel k, (int)(h * size), h outside [0, 1), h
 
-struct __align__(16) StripSmem {
+template <bool REJ>
+struct __align__(16) StripSmemT {
 	union {
 		float4 S[SH][SW];      // sampled current colour in YCoCg (phase 1 output)
 		uint2 craw[CRH][RW];   // raw colour texels (cp.async target, phase 1 input)
 	} u;
 	uint2 vraw[VRH][RW];
-	float dtile[TH][TW];   // current depth of the tile's pixels (rejection variants with depth culling)
+	float dtile[REJ ? TH : 1][TW];  // current depth of the tile's pixels (rejection variants with depth culling)
 	VelT vrow[TH];
 	VelT vcol[TW];
 	AxisT roww[TH];
 	AxisT colw[TW];
 	ColT crow[SH];
 	ColT ccol[SW];
+	unsigned int colok[2], rowok;         // uniform-motion votes: footprint columns of each tile half interior; bit wy: rows of warp row wy interior and regular
 	unsigned long long mbar;              // completion barrier of the bulk copies that stage the raw tiles
 	unsigned long long wmask[2][TH + 4];  // [half][r], bit c: velocity.w != 0 at texel (x0 + 32 half - 2 + c, y0 - 2 + r), clamped to the image
 };
-static_assert(sizeof(StripSmem) <= 75 * 1024, "three CTAs per SM");
+static_assert(sizeof(StripSmemT<true>) <= 75 * 1024, "three CTAs per SM");
 
 // d = a * b + c with a, b fp16 and c, d fp32 (FHFMA): the product of two halves is exact in fp32
 __device__ __forceinline__ float fhfma(__half a, __half b, float c) {
@@ -163,13 +165,42 @@ __device__ __forceinline__ void stage_tile(const Img& im, uint2 (*dst)[RW], int 
 	}
 }
 
+// The 4 x 4 (with REJ: 6 x 6 alpha ring) history texels a strip's window starts from, requested early (before the barrier that
+// ends phase 1) on uniform-motion warps so that their DRAM latency is hidden behind the tile write-back.
+template <bool REJ>
+struct Win0 {
+	uint2 q[16];
+	unsigned int e[8], t[6];  // (unused without REJ)
+};
+template <bool REJ>
+__device__ __forceinline__ void load_win0(Win0<REJ>& w, const unsigned char* p, const unsigned int hpitch) {
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const uint2* hp = reinterpret_cast<const uint2*>(p + i * hpitch);
+		w.q[4 * i] = __ldg(hp); w.q[4 * i + 1] = __ldg(hp + 1); w.q[4 * i + 2] = __ldg(hp + 2); w.q[4 * i + 3] = __ldg(hp + 3);
+	}
+	if (REJ) {
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			w.e[2 * i] = __ldg(reinterpret_cast<const unsigned int*>(p + i * hpitch - 4));
+			w.e[2 * i + 1] = __ldg(reinterpret_cast<const unsigned int*>(p + i * hpitch + 36));
+		}
+#pragma unroll
+		for (int j = 0; j < 6; ++j) w.t[j] = __ldg(reinterpret_cast<const unsigned int*>(p - hpitch - 4 + 8 * j));
+	}
+}
+
 // ---- phase 2: one column strip per thread ---------------------------------------------------------------------------------
 // FAST = the tile's motion is uniform (every staged velocity texel bit-identical, no mover near, all footprints interior, footprint
 // rows advancing one per pixel row): history coordinates and Catmull-Rom weights come from the per-row / per-column tables, and the
 // window never restarts. The arithmetic is the very same as in the general path (same functions of the same inputs).
 template <bool REJ, bool ALPHA, bool FAST, int UNR>
-__device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
-                                             const float fix_band, const int x0, const int y0, const int rows_valid, const int warp, const int lane) {
+__device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmemT<REJ>& sm, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
+                                             const float fix_band, const int x0, const int y0, const int rows_valid, const int warp, const int lane,
+                                             const Win0<REJ>& w0) {
+	// Request a uniform strip's first window before the barrier that ends phase 1? Measured on B200: +0.7 % for the rejection variants
+	// (128 registers), -1.5 % for the plain ones (the 32 registers it pins do not fit the 80-register cap).
+	constexpr bool EARLY_WIN = REJ;
 	const TaaParameters& P = A.ubo.param[0];
 	unsigned int* st = A.status;
 	const int W = A.out_w, H = A.out_h;
@@ -236,22 +267,12 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 		if (REJ) f_velz = __low2float(h2(sm.vraw[0][0].y));
 		const int K = sm.roww[r0].k - 1;
 		hoff = (unsigned int)(K - A.history_in.y0) * hpitch + (unsigned int)(cw.k - 1) * 8u;
-		const unsigned char* p = hbase + hoff;
-		uint2 q[16];
-#pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			const uint2* hp = reinterpret_cast<const uint2*>(p + i * hpitch);
-			q[4 * i] = __ldg(hp); q[4 * i + 1] = __ldg(hp + 1); q[4 * i + 2] = __ldg(hp + 2); q[4 * i + 3] = __ldg(hp + 3);
-		}
+		Win0<REJ> wl;
+		if (!EARLY_WIN) load_win0<REJ>(wl, hbase + hoff, hpitch);
+		const Win0<REJ>& ww = EARLY_WIN ? w0 : wl;  // EARLY_WIN: requested before the barrier that ends phase 1
+		const uint2* q = ww.q;
 		if (REJ) {
-			unsigned int e[8], t[6];
-#pragma unroll
-			for (int i = 0; i < 4; ++i) {
-				e[2 * i] = __ldg(reinterpret_cast<const unsigned int*>(p + i * hpitch - 4));
-				e[2 * i + 1] = __ldg(reinterpret_cast<const unsigned int*>(p + i * hpitch + 36));
-			}
-#pragma unroll
-			for (int j = 0; j < 6; ++j) t[j] = __ldg(reinterpret_cast<const unsigned int*>(p - hpitch - 4 + 8 * j));
+			const unsigned int *e = ww.e, *t = ww.t;
 			or0 = (t[0] | t[1] | t[2]) | (t[3] | t[4] | t[5]);
 			or1 = (q[0].y | q[1].y | q[2].y) | (q[3].y | e[0] | e[1]);
 			or2 = (q[4].y | q[5].y | q[6].y) | (q[7].y | e[2] | e[3]);
@@ -263,7 +284,13 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmem& sm
 		hr2 = hfilter<REJ>(q[8], q[9], q[10], q[11], axs.w);
 		hr3 = hfilter<REJ>(q[12], q[13], q[14], q[15], axs.w);
 		hoff += 4u * hpitch;
-		if (REJ && P.mDepthCulling) f_hd = fetch_r32f(A.history_depth, W, H, f_tx, sm.roww[r0].tc, st);
+		if (REJ && P.mDepthCulling) {
+			f_hd = fetch_r32f(A.history_depth, W, H, f_tx, sm.roww[r0].tc, st);
+			// consume the load HERE: a raw load result carried into the loop makes its first use in the loop body wait on the load's
+			// scoreboard in every iteration, and that scoreboard is shared with the look-ahead loads issued just before (measured: 19 %
+			// of the kernel's stall samples on that one FADD)
+			f_hd = __fadd_rn(f_hd, 0.0f);  // (an arithmetic no-op ptxas keeps: -0 + 0 = +0 is the only change, immaterial to the depth test)
+		}
 	}
 
 #pragma unroll UNR
@@ -574,6 +601,8 @@ __global__ void __launch_bounds__(NT, MINB)
 taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
                          unsigned int* __restrict__ fix_count_next, const float fix_band, const bool use_bulk) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
+	using StripSmem = StripSmemT<REJ>;
+	constexpr bool EARLY_WIN = REJ;  // see strip_phase2
 	StripSmem& sm = *reinterpret_cast<StripSmem*>(smem_raw);
 	const TaaParameters& P = A.ubo.param[0];
 	unsigned int* st = A.status;
@@ -653,28 +682,9 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 	__syncthreads();  // tables, (mbarrier initialised,) cp.async data of all threads
 	if (bulk) mbar_wait(&sm.mbar, 0u);
 
-	// ---- warm L1 with the history rows the strips start from (the window of a strip's first pixel is the one gather nothing hides) ----
-	// A hint only: the position is guessed from the tile's first velocity texel.
-	{
-		const float2 vg = __half22float2(h2(sm.vraw[0][0].x));
-		const int wx = warp & 1, wy = warp >> 1;
-		const int r0 = min(wy * RPT, max(rows_valid - 1, 0));
-		const float hu = sm.vcol[wx * 32 + lane].c - vg.x, hv = sm.vrow[r0].c - vg.y;
-		const int kx = (int)fminf(fmaxf(floorf(hu * fW - 0.5f) - 1.0f, 0.0f), fW - 4.0f);
-		const int ky = (int)fminf(fmaxf(floorf(hv * fH - 0.5f) - 1.0f, 0.0f), fH - 1.0f);
-		const int rlo = max(0, A.history_in.y0), rhi = min(H - 1, A.history_in.y0 + A.history_in.rows - 1);
-#pragma unroll
-		for (int i = 0; i < 5; ++i) {
-			const int gy = iclamp(ky + i, rlo, rhi);
-			const unsigned char* p = A.history_in.p + (size_t)(gy - A.history_in.y0) * (size_t)A.history_in.pitch + (size_t)kx * 8u;
-			asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-			asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 24));
-		}
-	}
-
-	// ---- is the tile's motion uniform? (vote, taken at the barrier inside phase 1) -------------------
-	// Every staged velocity texel bit-identical and finite, no mover within two texels of the tile, every history footprint of the
-	// tile interior to the image / band buffer, footprint rows advancing by exactly one per pixel row.
+	// ---- is the motion uniform? (votes, taken at the barrier inside phase 1) -------------------------
+	// Tile-wide: every staged velocity texel bit-identical and finite, no mover within two texels of the tile. Per warp (32 columns x 8
+	// rows): every history footprint interior to the image / band buffer, footprint rows advancing by exactly one per pixel row.
 	bool vote = true;
 	{
 		const uint2 vref = sm.vraw[0][0];
@@ -687,7 +697,7 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		if (REJ && P.mDynamicAntiGhosting) vote = vote && (vref.y & 0x7fff0000u) == 0u;  // no mover within two texels of the tile
 		const int hlo = max(0, A.history_in.y0), hhi = min(H - 1, A.history_in.y0 + A.history_in.rows - 1);
 		const int ring = REJ ? 1 : 0;
-		if (tid < TW + rows_valid) {
+		if (tid < TW + TH) {  // warps 0, 1: the columns of the two tile halves; warp 2: the rows
 			const float2 vxy = __half22float2(h2(vref.x));
 			AxisT t;
 			if (tid < TW) {
@@ -695,22 +705,35 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 				const AxisW a = catmull_axis(hu, fW, invw);
 				t.w[0] = a.w[0]; t.w[1] = a.w[1]; t.w[2] = a.w[2]; t.w[3] = a.w[3];
 				t.k = a.k; t.tc = (int)(hu * fW); t.outside = (hu < 0.f || hu >= 1.f) ? 1u : 0u; t.h = hu;
-				vote = vote && a.k - 1 - ring >= 0 && a.k + 2 + ring <= W - 1;
+				const bool ok = a.k - 1 - ring >= 0 && a.k + 2 + ring <= W - 1;
 				sm.colw[tid] = t;
+				const bool all_ok = __all_sync(0xffffffffu, ok);
+				if (lane == 0) sm.colok[warp] = all_ok ? 1u : 0u;
 			} else {
 				const int r = tid - TW;
-				const float hv = sm.vrow[r].c - vxy.y;
-				const AxisW a = catmull_axis(hv, fH, invh);
-				t.w[0] = a.w[0]; t.w[1] = a.w[1]; t.w[2] = a.w[2]; t.w[3] = a.w[3];
-				t.k = a.k; t.tc = (int)(hv * fH); t.outside = (hv < 0.f || hv >= 1.f) ? 1u : 0u; t.h = hv;
-				vote = vote && a.k - 1 - ring >= hlo && a.k + 3 <= hhi;  // (row k + 3 is the look-ahead row of the window)
-				if (r + 1 < rows_valid) vote = vote && catmull_axis(sm.vrow[r + 1].c - vxy.y, fH, invh).k == a.k + 1;
-				sm.roww[r] = t;
+				bool ok = true;
+				if (r < rows_valid) {
+					const float hv = sm.vrow[r].c - vxy.y;
+					const AxisW a = catmull_axis(hv, fH, invh);
+					t.w[0] = a.w[0]; t.w[1] = a.w[1]; t.w[2] = a.w[2]; t.w[3] = a.w[3];
+					t.k = a.k; t.tc = (int)(hv * fH); t.outside = (hv < 0.f || hv >= 1.f) ? 1u : 0u; t.h = hv;
+					ok = a.k - 1 - ring >= hlo && a.k + 3 <= hhi;  // (row k + 3 is the look-ahead row of the window)
+					if (r + 1 < rows_valid && ((r + 1) & (RPT - 1)) != 0) ok = ok && catmull_axis(sm.vrow[r + 1].c - vxy.y, fH, invh).k == a.k + 1;
+					sm.roww[r] = t;
+				}
+				const unsigned int bad = __ballot_sync(0xffffffffu, !ok);
+				if (lane == 0) {
+					unsigned int m = 0u;
+#pragma unroll
+					for (int w = 0; w < WY; ++w) m |= ((bad >> (w * RPT)) & ((1u << RPT) - 1u)) == 0u ? (1u << w) : 0u;
+					sm.rowok = m;
+				}
 			}
 		}
 	}
 
 	bool fast;
+	Win0<REJ> w0;
 	// ---- phase 1: sampled current colour in YCoCg, in place ----------------------------------------
 	// A warp takes whole tile rows (warp, warp + 8, ...); a lane owns tile columns lane and lane + 32; columns 64 and 65 go to the
 	// first threads. Everything is read into registers first: the sampled tile overwrites the raw one.
@@ -739,11 +762,13 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 			ve = sample_ycocg(*reinterpret_cast<const uint2*>(cr + (cy.m + cx.m)), *reinterpret_cast<const uint2*>(cr + (cy.m + cx.n)),
 			                  *reinterpret_cast<const uint2*>(cr + (cy.n + cx.m)), __float2half_rn(cx.p), __float2half_rn(cy.p));
 		}
-		fast = __syncthreads_and(vote ? 1 : 0) != 0;
+		const bool uni = __syncthreads_and(vote ? 1 : 0) != 0;
+		fast = uni && sm.colok[warp & 1] != 0u && ((sm.rowok >> (warp >> 1)) & 1u) != 0u;  // this warp's strips
+		const bool cta_fast = uni && sm.colok[0] != 0u && sm.colok[1] != 0u && sm.rowok == (1u << WY) - 1u;
 		// Movers (velocity.w != 0, fwd_geometry.frag:289-295) are what the 5-tap anti-ghosting test looks for (taa.comp:796-811). Every tap's
 		// bilinear footprint lies inside the 5x5 texels around the pixel; where all of them have w == +-0 the taps return w == 0 exactly.
 		// Only the general path needs the mask (a uniform tile has none); it is read after the next barrier.
-		if (REJ && !fast && P.mDynamicAntiGhosting) {
+		if (REJ && !cta_fast && P.mDynamicAntiGhosting) {
 			for (int r = warp; r < rows_valid + 4; r += NWARP) {
 				row_off(A.velocity, iclamp(y0 - 2 + r, 0, H - 1), st);  // reports rows a band buffer does not hold
 				const unsigned int wa = sm.vraw[r][lane].y & 0x7fff0000u, wb = sm.vraw[r][lane + 32].y & 0x7fff0000u;
@@ -765,14 +790,28 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		}
 		if (tid < 2 * nrows) sm.u.S[tid >> 1][TW + (tid & 1)] = make_float4(ve.x, ve.y, ve.z, 0.f);
 	}
+	// the window a uniform-motion strip starts from: requested before the barrier, consumed after it
+	if (EARLY_WIN && fast && (warp >> 1) * RPT < rows_valid)
+		load_win0<REJ>(w0, A.history_in.p + ((unsigned int)(sm.roww[(warp >> 1) * RPT].k - 1 - A.history_in.y0) * (unsigned int)A.history_in.pitch +
+		                                    (unsigned int)(sm.colw[(warp & 1) * 32 + lane].k - 1) * 8u), (unsigned int)A.history_in.pitch);
 	__syncthreads();
+	// keep the compiler from consuming (= waiting for) the window texels before the barrier
+#pragma unroll
+	for (int i = 0; i < 16; i += 4)
+		asm volatile("" : "+r"(w0.q[i].x), "+r"(w0.q[i].y), "+r"(w0.q[i + 1].x), "+r"(w0.q[i + 1].y), "+r"(w0.q[i + 2].x), "+r"(w0.q[i + 2].y), "+r"(w0.q[i + 3].x),
+		             "+r"(w0.q[i + 3].y));
+	if (REJ) {
+		asm volatile("" : "+r"(w0.e[0]), "+r"(w0.e[1]), "+r"(w0.e[2]), "+r"(w0.e[3]), "+r"(w0.e[4]), "+r"(w0.e[5]), "+r"(w0.e[6]), "+r"(w0.e[7]));
+		asm volatile("" : "+r"(w0.t[0]), "+r"(w0.t[1]), "+r"(w0.t[2]), "+r"(w0.t[3]), "+r"(w0.t[4]), "+r"(w0.t[5]));
+	}
 
-	if (fast) strip_phase2<REJ, ALPHA, true, UNR>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane);
-	else strip_phase2<REJ, ALPHA, false, UNR>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane);
+	if (fast) strip_phase2<REJ, ALPHA, true, UNR>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane, w0);
+	else strip_phase2<REJ, ALPHA, false, UNR>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane, w0);
 }
 
 template <bool REJ, bool ALPHA, int MINB, int UNR>
 cudaError_t launch_variant(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, float band, cudaStream_t stream) {
+	using StripSmem = StripSmemT<REJ>;
 	auto kern = taa_resolve_strip_kernel<REJ, ALPHA, MINB, UNR>;
 	static bool configured = false;  // per variant
 	if (!configured) {
