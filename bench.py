@@ -181,6 +181,12 @@ def run_single(args):
     NSETS = 4
     sc = SyntheticScene(W, H, device=dev, with_aux=False)
     frames = [sc.frame(n) for n in range(NSETS)]
+    assert args.motion == "pan" or args.kernel_only, "--motion varying is a kernel-only tuning aid; the bench line is measured on the pan of SURVEY 8d"
+    if args.motion == "varying":  # tuning aid: a smoothly varying velocity field (no tile is uniform, no column shares its history u)
+        yy, xx = torch.meshgrid(torch.arange(H, device=dev, dtype=torch.float32), torch.arange(W, device=dev, dtype=torch.float32), indexing="ij")
+        gain = 1.0 + 0.25 * torch.sin(xx * 0.011) * torch.cos(yy * 0.013)
+        for f in frames:
+            f.velocity[..., 0:2] = (f.velocity[..., 0:2].float() * gain[..., None]).half()
     ctx = host.TaaContext((W, H), flags=flags)
     hist = [torch.zeros(H, W, 4, dtype=torch.float16, device=dev) for _ in range(2)]
     result = torch.zeros(H, W, 4, dtype=torch.float16, device=dev)
@@ -227,7 +233,7 @@ def run_single(args):
     if args.kernel_only:  # tuning aid: device-timed kernel numbers only
         print(json.dumps({"kernel_only": True, "config": cfg_id, "ms_per_step": round(ms_per_step, 5), "Mpixels/s": round(mpx_s, 1),
                           "frac": round(achieved / peak, 4), "gpu_launches": int(launches), "fixup_pixels": ctx.fixup_pixels(),
-                          "variant": os.environ.get("TAA_TUNED_VARIANT")}), flush=True)
+                          "variant": os.environ.get("TAA_TUNED_VARIANT"), "motion": args.motion}), flush=True)
         return
     # ---- e2e: host buffers through the invokee (taa<CF>::render path), H2D + D2H inside the timed region ----
     t = host.Taa(3, flags=flags)
@@ -292,7 +298,7 @@ def run_single(args):
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                      "traffic_source": traffic_src, "algorithmic_bytes": BYTES_PER_PX[cfg_id] * px,
                      "peak_source": peak_src, "bytes_per_px": BYTES_PER_PX[cfg_id],
-                     "kernel": "taa_resolve_tuned_kernel + taa_resolve_fixup_kernel (one step)" if not args.exact else "taa_resolve_generic_kernel"},
+                     "kernel": "taa_resolve_strip_kernel + taa_resolve_fixup_kernel (one step)" if not args.exact else "taa_resolve_generic_kernel"},
         "cpu_baseline": {"value": round(cpu_mpx, 3), "unit": "Mpixels/s", "cores": cores, "kind": cpu_kind, "sample": sample},
         "e2e": {"value": round(e2e_mpx, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "fps": round(e2e_steps / e2e_dt, 1), "path": "taa_invokee_frame_host: pinned host G-buffer -> H2D -> render() -> D2H of the final image, 3 frames in flight",
@@ -309,6 +315,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3])
+    ap.add_argument("--motion", default="pan", choices=["pan", "varying"], help="varying: perturb the synthetic velocity field (kernel-only tuning aid; the bench line is 'pan', SURVEY 8d)")
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and CPU legs (tuning aid; not a bench line)")

@@ -15,3 +15,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:t
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:taa_resolve -s 8 -c 2 -f -o gpurun_out/prof_resolve python bench.py --kernel-only --steps 8 --warmup 4 > gpurun_out/ncu_full.log 2>&1
 fi
 tail -60 gpurun_out/round.log
+if [ "${NCU:-1}" = "1" ]; then
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:taa_resolve -s 8 -c 2 -f -o gpurun_out/prof_resolve_c3 python bench.py --kernel-only --config 3 --steps 8 --warmup 4 > gpurun_out/ncu_full_c3.log 2>&1
+fi
