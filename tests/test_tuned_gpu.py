@@ -291,3 +291,64 @@ def test_fixup_pass_is_bit_exact(oracle, sw):
             r = mismatch_report(k, ref[k], got[k])
             assert r is None, r
         assert (ref["mask"] == got["mask"]).all()
+
+
+# ---- paths of the strip kernel (taa_resolve_strip.cu) ------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", ["config2", "config3"])
+def test_smoothly_varying_motion_runs_the_general_strip_path(oracle, cfg):
+    """No tile is uniform and no column keeps its history u: window restarts, per-pixel weights, the mover mask of config 3."""
+    w, h = 320, 200
+    sc = SyntheticScene(w, h)
+    f0, f1 = sc.frame(2), sc.frame(3)
+    ins = np_inputs(f1)
+    yy, xx = np.meshgrid(np.arange(h, dtype=np.float32), np.arange(w, dtype=np.float32), indexing="ij")
+    gain = 1.0 + 0.25 * np.sin(xx * 0.11) * np.cos(yy * 0.13)
+    vel = ins["velocity"].astype(np.float32)
+    vel[..., 0:2] *= gain[..., None]
+    ins["velocity"] = vel.astype(np.float16)
+    u = configs.uniforms_for(CFG[cfg](), f1.jitter_ndc)
+    check_tuned(oracle, u, ins, random_history(h, w, 21), hist_depth=f0.depth.numpy())
+
+
+@pytest.mark.parametrize("pan", [(0.0, 0.0), (3.0, 0.5), (-2.25, -1.75), (0.5, 7.0), (40.0, -30.0)])
+def test_uniform_motion_tiles(oracle, pan):
+    """Uniform-motion fast path: zero motion, sub-pixel phases, footprints that leave the image on every side, no mover in the scene."""
+    w, h = 256, 160
+    sc = SyntheticScene(w, h, pan_px=pan, mover_px=pan)  # the foreground quad moves with the background: one velocity everywhere
+    f0, f1 = sc.frame(6), sc.frame(7)
+    ins = np_inputs(f1)
+    ins["velocity"][..., 0:2] = ins["velocity"][h // 2, w // 2, 0:2]  # bit-identical texels, whatever the generator rounds to
+    ins["velocity"][..., 3] = 0
+    for cfg in ("config2", "config3"):
+        u = configs.uniforms_for(CFG[cfg](), f1.jitter_ndc)
+        check_tuned(oracle, u, ins, random_history(h, w, 22), hist_depth=f0.depth.numpy())
+
+
+def test_uniform_tiles_next_to_a_mover_and_history_alpha(oracle):
+    """Config 3: a history whose alpha marks a moving region (anti-ghost ring test) under uniform motion, and velocity.w set in one tile."""
+    w, h = 256, 160
+    sc = SyntheticScene(w, h, pan_px=(2.0, 1.0), mover_px=(2.0, 1.0))
+    f0, f1 = sc.frame(3), sc.frame(4)
+    ins = np_inputs(f1)
+    ins["velocity"][..., 0:2] = ins["velocity"][h // 2, w // 2, 0:2]
+    ins["velocity"][..., 3] = 0
+    ins["velocity"][40:56, 70:90, 3] = 1.0   # a mover patch: its tile and the neighbours within two texels take the general path
+    hist = random_history(h, w, 23)
+    hist[..., 3] = 0
+    hist[60:100, 100:180, 3] = 1.0           # dynamic mask of the previous frame
+    hist[10, 5:9, 3] = 1.0
+    u = configs.uniforms_for(CFG["config3"](), f1.jitter_ndc)
+    check_tuned(oracle, u, ins, hist, hist_depth=f0.depth.numpy())
+
+
+def test_tile_kernel_variant_in_a_subprocess():
+    """The 32x32-tile kernel (TAA_TUNED_VARIANT=tile, the A/B partner of the strip kernel) honours the same contract."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, TAA_TUNED_VARIANT="tile")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_tuned_gpu.py"), "-q", "-x", "-m", "gpu", "-k",
+                        "test_single_frame or test_tiny_and_ragged_sizes or test_extreme_and_non_finite_motion or test_fixup_pass_is_bit_exact"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
