@@ -119,7 +119,11 @@ class ShardedTaa:
         self.xchg = HaloExchanger(L, group)
         self.compute = torch.cuda.Stream(device=self.device)
         self.comm = torch.cuda.Stream(device=self.device)
-        self.ev_boundary = torch.cuda.Event()
+        # the boundary strips gate the exchange: each gets its own high-priority stream and runs beside the interior resolve (a 20-row
+        # strip is a quarter of a wave of CTAs; back to back with its fix-up pass it would cost a CTA lifetime of an otherwise idle GPU)
+        self.s_boundary = [torch.cuda.Stream(device=self.device, priority=-1) for _ in self.boundary]
+        self.ev_boundary = [torch.cuda.Event() for _ in self.boundary]
+        self.ev_start = torch.cuda.Event()
         self.ev_comm = torch.cuda.Event()
         self.parity = 0
         self._pending = []
@@ -138,10 +142,14 @@ class ShardedTaa:
             kw["history_depth"] = (history_depth, in_y0)
         with torch.cuda.stream(self.compute):
             self.compute.wait_event(self.ev_comm)  # halos of `hin` (written by the previous exchange) must have landed
-            for c in self.boundary:
-                c.resolve(uniforms, stream=self.compute, **kw)
-            self.ev_boundary.record(self.compute)
-            if self.interior is not None:
+            self.ev_start.record(self.compute)     # ... and everything the caller queued on `compute` (input copies) is ordered before
+        for c, sb, ev in zip(self.boundary, self.s_boundary, self.ev_boundary):
+            with torch.cuda.stream(sb):
+                sb.wait_event(self.ev_start)
+                c.resolve(uniforms, stream=sb, **kw)
+                ev.record(sb)
+        if self.interior is not None:
+            with torch.cuda.stream(self.compute):
                 self.interior.resolve(uniforms, stream=self.compute, **kw)
         if self.world > 1:
             if self.replicate:
@@ -151,7 +159,8 @@ class ShardedTaa:
                     self.ev_comm.record(self.compute)
             else:
                 with torch.cuda.stream(self.comm):
-                    self.comm.wait_event(self.ev_boundary)
+                    for ev in self.ev_boundary:
+                        self.comm.wait_event(ev)
                     for w in self._pending:
                         w.wait()
                     self._pending = self.xchg.exchange(hout)
@@ -159,6 +168,9 @@ class ShardedTaa:
                         w.wait()
                     self._pending = []
                     self.ev_comm.record(self.comm)
+        with torch.cuda.stream(self.compute):  # join: what follows on `compute` (next step, result copies) sees the whole band
+            for ev in self.ev_boundary:
+                self.compute.wait_event(ev)
         self.parity ^= 1
 
     def poll(self) -> int:
