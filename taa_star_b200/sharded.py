@@ -127,6 +127,8 @@ class ShardedTaa:
         self.ev_comm = torch.cuda.Event()
         self.parity = 0
         self._pending = []
+        self._capturing = False
+        self._ev_comm_captured = False
 
     @property
     def launch_count(self):
@@ -141,7 +143,10 @@ class ShardedTaa:
         if history_depth is not None:
             kw["history_depth"] = (history_depth, in_y0)
         with torch.cuda.stream(self.compute):
-            self.compute.wait_event(self.ev_comm)  # halos of `hin` (written by the previous exchange) must have landed
+            if not self._capturing:  # (a captured step ends with the exchange joined into `compute`: replays are ordered by the stream)
+                if self._ev_comm_captured:  # an event last recorded inside a capture cannot be waited on outside of it
+                    self.ev_comm, self._ev_comm_captured = torch.cuda.Event(), False
+                self.compute.wait_event(self.ev_comm)  # halos of `hin` (written by the previous exchange) must have landed
             self.ev_start.record(self.compute)     # ... and everything the caller queued on `compute` (input copies) is ordered before
         for c, sb, ev in zip(self.boundary, self.s_boundary, self.ev_boundary):
             with torch.cuda.stream(sb):
@@ -171,7 +176,26 @@ class ShardedTaa:
         with torch.cuda.stream(self.compute):  # join: what follows on `compute` (next step, result copies) sees the whole band
             for ev in self.ev_boundary:
                 self.compute.wait_event(ev)
+            if self._capturing and self.world > 1:
+                self.compute.wait_event(self.ev_comm)
         self.parity ^= 1
+
+    def capture_step(self, *args, **kw) -> "torch.cuda.CUDAGraph":
+        """Captures one step() (all launches on the three resolve streams, the NCCL halo exchange and their dependencies) into a CUDA
+        graph on `compute`; the caller replays it on `compute`. A step costs ~0.2-0.3 ms of host time to enqueue, more than the GPU needs
+        at 4+ ranks. The graph bakes in this step's arguments (uniforms, buffers, history parity, the contexts' fix-up counter parity):
+        capture one graph per distinct step of a cycle of EVEN length and replay them in capture order. Capturing does not run the step
+        but does advance the host-side parities, exactly as the replay will find them."""
+        assert not self._pending
+        g = torch.cuda.CUDAGraph()
+        self._capturing = True
+        try:
+            with torch.cuda.graph(g, stream=self.compute, capture_error_mode="thread_local"):
+                self.step(*args, **kw)
+        finally:
+            self._capturing = False
+            self._ev_comm_captured = True
+        return g
 
     def poll(self) -> int:
         st = 0
@@ -208,10 +232,31 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
         sh.step(u or unis[i % NSETS], f.color, f.depth, f.velocity, L.iy0, history_depth=fp.depth if cfg_id == 3 else None)
 
     step(0, u0)
-    for i in range(1, args.warmup + 1):
+    nwarm = max(args.warmup, 1)
+    nwarm += (2 * NSETS - (nwarm + 1) % (2 * NSETS)) % (2 * NSETS)  # the next step index is a multiple of the cycle (frame set x history parity)
+    for i in range(1, nwarm + 1):
         step(i)
     torch.cuda.synchronize()
     assert sh.poll() == abi.TAA_OK, "halo overflow during warm-up"
+    graphs = None
+    if os.environ.get("TAA_SHARDED_GRAPHS", "1") != "0":  # one CUDA graph per step of the cycle (kernels + NCCL exchange): see capture_step
+        graphs = []
+        launches_c0 = sh.launch_count  # (the contexts count launches as they record them: a replay repeats what the capture recorded)
+        for k in range(2 * NSETS):
+            i = nwarm + 1 + k
+            f, fp = frames[i % NSETS], frames[(i - 1) % NSETS]
+            g = sh.capture_step(unis[i % NSETS], f.color, f.depth, f.velocity, L.iy0, history_depth=fp.depth if cfg_id == 3 else None)
+            with torch.cuda.stream(sh.compute):
+                g.replay()  # run it once: device state follows the host-side parities
+            graphs.append(g)
+        torch.cuda.synchronize()
+        assert sh.poll() == abi.TAA_OK
+        launches_per_cycle = sh.launch_count - launches_c0
+        nwarm += 2 * NSETS
+
+        def step(i, u=None):  # noqa: F811
+            with torch.cuda.stream(sh.compute):
+                graphs[(i - (nwarm + 1)) % (2 * NSETS)].replay()
     clocks = ClockSampler(local) if rank == 0 else None
     launches0 = sh.launch_count
     dist.barrier()
@@ -220,18 +265,25 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
     if clocks:
         clocks.region(True)
     ev0.record(sh.compute)
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
-        step(i + args.warmup + 1)
-    sh.compute.wait_event(sh.ev_comm)
+        step(i + nwarm + 1)
+    if graphs is None:  # (a captured step ends with the exchange joined into `compute`)
+        sh.compute.wait_event(sh.ev_comm)
     ev1.record(sh.compute)
+    host_ms_per_step = (time.perf_counter() - t_host0) * 1e3 / args.steps  # time to ENQUEUE a step (a step is host-bound if this ~ ms_per_step)
     torch.cuda.synchronize()
+    if graphs is not None:  # complete the cycle, so that the device-side state matches the host-side parities again
+        for i in range(args.steps, args.steps + (-args.steps) % (2 * NSETS)):
+            step(i + nwarm + 1)
+        torch.cuda.synchronize()
     dist.barrier()
     if clocks:
         clocks.region(False)
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    launches = torch.tensor([sh.launch_count - launches0], device=dev)
+    launches = torch.tensor([sh.launch_count - launches0 if graphs is None else launches_per_cycle * args.steps // (2 * NSETS)], device=dev)
     dist.all_reduce(launches)
     # kernel-only time of this rank's interior + boundary launches is not separable from the exchange here; the roofline entry uses
     # the per-step time of the whole sharded step (conservative).
@@ -275,11 +327,12 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
     if rank == 0:
         line = {
             "metric": "resolved Mpixels/s", "value": round(mpx_s, 1), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": round(ms_per_step, 5), "host_enqueue_ms_per_step": round(host_ms_per_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": round(1e3 / ms_per_step, 1),
             "config": {"workload": f"{W}x{H} TAA resolve sharded in {world} row bands, BASELINE configs[3] (config {cfg_id} settings)",
                        "arithmetic": "exact general kernel" if args.exact else "tuned kernel + exact fix-up pass", "halo_rows": halo,
                        "exchange": "NCCL send/recv of 2 x halo rows of history per neighbour per frame, overlapped with the interior resolve",
+                       "launch": "one CUDA graph per step (kernels on 3 streams + the NCCL exchange)" if graphs is not None else "eager",
                        "l2": f"inputs larger than L2: {NSETS} frame sets rotated, history ping-pong"},
             "gpu_launches": int(launches.item()),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
@@ -290,5 +343,19 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
             "clocks": clocks.result() if clocks else None,
         }
         print(json.dumps(line), flush=True)
+    # tear-down: graphs that captured NCCL work go first; the process-group destructor has been seen to hang behind them, so it gets
+    # a deadline (the line is printed and flushed by now)
+    import gc
+    import sys
+    import threading
+    graphs = None
+    step = None
+    gc.collect()
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(20.0)
+    if t.is_alive():
+        os._exit(0)
