@@ -129,6 +129,7 @@ class ShardedTaa:
         self._pending = []
         self._capturing = False
         self._ev_comm_captured = False
+        self._comm_in_capture = False
 
     @property
     def launch_count(self):
@@ -142,20 +143,31 @@ class ShardedTaa:
                   history_out=(hout, self.hist_y0), result=(self.result, L.y0))
         if history_depth is not None:
             kw["history_depth"] = (history_depth, in_y0)
+        exchanging = self.world > 1 and not self.replicate
+        # The interior rows [y0 + halo, y1 - halo) never read a halo row (motion bound + filter footprint < halo): the interior resolve of
+        # step n+1 depends on this rank's own step-n kernels only, NOT on exchange n. It is handed the band rows of the history alone, so a
+        # read beyond them is reported (TAA_E_HALO_OVERFLOW) instead of racing with the exchange. Only the boundary strips wait for the halos.
+        kw_int = kw
+        if exchanging:
+            kw_int = dict(kw, history_in=(hin[L.y0 - self.hist_y0: L.y1 - self.hist_y0], L.y0), history_out=(hout[L.y0 - self.hist_y0: L.y1 - self.hist_y0], L.y0))
         with torch.cuda.stream(self.compute):
-            if not self._capturing:  # (a captured step ends with the exchange joined into `compute`: replays are ordered by the stream)
-                if self._ev_comm_captured:  # an event last recorded inside a capture cannot be waited on outside of it
-                    self.ev_comm, self._ev_comm_captured = torch.cuda.Event(), False
-                self.compute.wait_event(self.ev_comm)  # halos of `hin` (written by the previous exchange) must have landed
-            self.ev_start.record(self.compute)     # ... and everything the caller queued on `compute` (input copies) is ordered before
+            self.ev_start.record(self.compute)  # everything queued on `compute` so far (input copies, the previous step) is ordered before
         for c, sb, ev in zip(self.boundary, self.s_boundary, self.ev_boundary):
             with torch.cuda.stream(sb):
                 sb.wait_event(self.ev_start)
+                if exchanging:  # halos of `hin` (written by the previous exchange) must have landed
+                    if self._capturing:
+                        if self._comm_in_capture:
+                            sb.wait_event(self.ev_comm)  # (first step of a capture: the previous graph ended with the exchange joined)
+                    else:
+                        if self._ev_comm_captured:  # an event last recorded inside a capture cannot be waited on outside of it
+                            self.ev_comm, self._ev_comm_captured = torch.cuda.Event(), False
+                        sb.wait_event(self.ev_comm)
                 c.resolve(uniforms, stream=sb, **kw)
                 ev.record(sb)
         if self.interior is not None:
             with torch.cuda.stream(self.compute):
-                self.interior.resolve(uniforms, stream=self.compute, **kw)
+                self.interior.resolve(uniforms, stream=self.compute, **kw_int)
         if self.world > 1:
             if self.replicate:
                 with torch.cuda.stream(self.compute):
@@ -173,11 +185,10 @@ class ShardedTaa:
                         w.wait()
                     self._pending = []
                     self.ev_comm.record(self.comm)
+                    self._comm_in_capture = self._capturing
         with torch.cuda.stream(self.compute):  # join: what follows on `compute` (next step, result copies) sees the whole band
             for ev in self.ev_boundary:
                 self.compute.wait_event(ev)
-            if self._capturing and self.world > 1:
-                self.compute.wait_event(self.ev_comm)
         self.parity ^= 1
 
     def capture_step(self, *args, **kw) -> "torch.cuda.CUDAGraph":
@@ -195,11 +206,15 @@ class ShardedTaa:
         self._capturing = True
         try:
             with torch.cuda.graph(g, stream=self.compute, capture_error_mode="thread_local"):
+                self._comm_in_capture = False
                 for a, k in steps:
                     self.step(*a, **k)
+                if self._comm_in_capture:  # every forked stream joins `compute` before the capture ends
+                    self.compute.wait_event(self.ev_comm)
         finally:
             self._capturing = False
-            self._ev_comm_captured = True
+            self._ev_comm_captured = self._comm_in_capture
+            self._comm_in_capture = False
         return g
 
     def poll(self) -> int:
