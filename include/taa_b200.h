@@ -403,6 +403,26 @@ TAA_API int  taa_invokee_frame_host(taa_invokee* t, int64_t frame_id, const taa_
                                     const float view[16], const float proj[16], float time_s,
                                     float cam_near, float cam_far, void* out_final_host);
 TAA_API int  taa_invokee_wait(taa_invokee* t, int64_t frame_id);
+/*
+ * ---- settings files: writeSettingsToIni / readSettingsFromIni, taa.hpp:1198-1339 ----
+ * The INI text of the reference's mINI dependency (external/include/mini/ini.h): sections TAA_Param_0, TAA_Param_1, TAA_Primary,
+ * TAA_Postprocess with the reference's key names (names are not case sensitive), value formats of source/IniUtil.cpp:52-56,104-109.
+ * An absent or empty value keeps the current setting. Pure host code.
+ * write: returns the size of the text including the terminating NUL (call with out = NULL to size the buffer), < 0 on error.
+ * read : `offsets` receives mDebugSampleOffsets (the current ones resized to max(1, size) vec2s, then the keys that are present) and
+ *        becomes s->jitter.mDebugSampleOffsets; offsets_cap counts vec2s.
+ *        A value that is not a number (where the reference's std::stoul / stol / stof would throw) gives TAA_E_INVALID_ARG; the valid
+ *        keys are applied all the same; taa_settings_ini_last_error() names the first offending key (thread-local).
+ */
+TAA_API int32_t taa_settings_write_ini(const TaaParameters params[2], const taa_invokee_settings* s, const TaaPostProcessPush* pp,
+                                       char* out, int32_t cap);
+TAA_API int  taa_settings_read_ini(const char* text, TaaParameters params[2], taa_invokee_settings* s, TaaPostProcessPush* pp,
+                                   float* offsets, int32_t offsets_cap);
+TAA_API const char* taa_settings_ini_last_error(void);
+/* the same on the invokee's own mParameters / settings / mPostProcessPushConstants (it owns the sample-offset storage) */
+TAA_API int32_t taa_invokee_write_settings_ini(taa_invokee* t, char* out, int32_t cap);
+TAA_API int  taa_invokee_read_settings_ini(taa_invokee* t, const char* text);
+
 /* pinned host allocation helpers for the host-buffer path */
 TAA_API void* taa_host_alloc(size_t bytes);
 TAA_API void  taa_host_free(void* p);

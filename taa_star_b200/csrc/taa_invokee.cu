@@ -199,6 +199,23 @@ TaaPostProcessPush* taa_invokee_postprocess(taa_invokee* t) { return t ? &t->mPo
 const TaaUniforms* taa_invokee_uniforms(const taa_invokee* t) { return t ? &t->mTaaUniforms : nullptr; }
 long long taa_invokee_launch_count(const taa_invokee* t) { return (t && t->ctx) ? taa_launch_count(t->ctx) : 0; }
 
+// writeSettingsToIni / readSettingsFromIni (taa.hpp:1198-1339) on the invokee's own members; taa_ini.cu holds the format
+int32_t taa_invokee_write_settings_ini(taa_invokee* t, char* out, int32_t cap) {
+	if (!t) return TAA_E_INVALID_ARG;
+	return taa_settings_write_ini(t->mParameters, &t->S, &t->mPostProcessPushConstants, out, cap);
+}
+int taa_invokee_read_settings_ini(taa_invokee* t, const char* text) {
+	if (!t || !text) return TAA_E_INVALID_ARG;
+	std::vector<float> tmp(2 * 4096, 0.f);
+	const int r = taa_settings_read_ini(text, t->mParameters, &t->S, &t->mPostProcessPushConstants, tmp.data(), 4096);
+	const int n = t->S.jitter.mDebugSampleOffsets == tmp.data() ? t->S.jitter.mDebugSampleOffsetsCount : 0;
+	if (n > 0) t->debugOffsets.assign(tmp.begin(), tmp.begin() + 2 * n);
+	t->S.jitter.mDebugSampleOffsets = t->debugOffsets.data();
+	t->S.jitter.mDebugSampleOffsetsCount = (int32_t)(t->debugOffsets.size() / 2);
+	if (r != TAA_OK) t->last_error = taa_settings_ini_last_error();
+	return r;
+}
+
 // get_jittered_projection_matrix — taa.hpp:243-259
 int taa_invokee_get_jittered_projection_matrix(taa_invokee* t, const float proj[16], int64_t frame, float out_proj[16], float out_jitter[2]) {
 	if (!t || !proj || !out_proj || t->in_w <= 0) return TAA_E_INVALID_ARG;

@@ -141,6 +141,33 @@ class TaaContext:
         return int(self._lib.taa_launch_count(self._h))
 
 
+def write_settings_ini(params, settings: "abi.taa_invokee_settings", post: "abi.TaaPostProcessPush") -> str:
+    """writeSettingsToIni (taa.hpp:1198-1265) on plain parameter blocks: params = (TaaParameters, TaaParameters). No GPU needed."""
+    lib = abi.load_library()
+    arr = (abi.TaaParameters * 2)(params[0], params[1])
+    n = lib.taa_settings_write_ini(arr, C.byref(settings), C.byref(post), None, 0)
+    buf = C.create_string_buffer(n)
+    lib.taa_settings_write_ini(arr, C.byref(settings), C.byref(post), buf, n)
+    return buf.value.decode()
+
+
+def read_settings_ini(text: str, params, settings: "abi.taa_invokee_settings", post: "abi.TaaPostProcessPush", max_offsets: int = 64):
+    """readSettingsFromIni (taa.hpp:1267-1339): updates params[0], params[1], settings and post in place; returns the list of
+    mDebugSampleOffsets (vec2 tuples). Keys that are absent or empty keep their current value. No GPU needed."""
+    lib = abi.load_library()
+    arr = (abi.TaaParameters * 2)(params[0], params[1])
+    offs = (C.c_float * (2 * max_offsets))()
+    st = lib.taa_settings_read_ini(text.encode(), arr, C.byref(settings), C.byref(post), offs, max_offsets)
+    C.memmove(C.byref(params[0]), C.byref(arr[0]), C.sizeof(abi.TaaParameters))
+    C.memmove(C.byref(params[1]), C.byref(arr[1]), C.sizeof(abi.TaaParameters))
+    n = settings.jitter.mDebugSampleOffsetsCount
+    out = [(offs[2 * i], offs[2 * i + 1]) for i in range(n)]
+    settings._offsets_keepalive = offs  # settings.jitter.mDebugSampleOffsets points into it
+    if st != abi.TAA_OK:
+        raise TaaError(st, lib.taa_settings_ini_last_error().decode())
+    return out
+
+
 def cas_setup(sharpness: float, out_w: int, out_h: int) -> TaaCasPush:
     """CasSetup as update() calls it (taa.hpp:965)."""
     pc = TaaCasPush()
@@ -278,6 +305,17 @@ class Taa:
         out = C.c_void_p()
         self._check(self._lib.taa_invokee_render(self._h, frame_id, _stream_ptr(stream), C.byref(out)), "render")
         return out.value
+
+    def writeSettingsToIni(self) -> str:  # taa.hpp:1198
+        n = self._lib.taa_invokee_write_settings_ini(self._h, None, 0)
+        buf = C.create_string_buffer(n)
+        self._lib.taa_invokee_write_settings_ini(self._h, buf, n)
+        return buf.value.decode()
+
+    def readSettingsFromIni(self, text: str):  # taa.hpp:1267
+        st = self._lib.taa_invokee_read_settings_ini(self._h, text.encode())
+        if st != abi.TAA_OK:
+            raise TaaError(st, self._lib.taa_settings_ini_last_error().decode())
 
     def duration(self) -> float:  # taa.hpp:367
         return float(self._lib.taa_invokee_duration(self._h))

@@ -110,3 +110,100 @@ def test_invokee_settings_defaults(taalib):
     with pytest.raises(Exception):
         host.Taa(1)  # static_assert(CF > 1), taa.hpp:1005
     t.close()
+
+
+# ---- settings files: writeSettingsToIni / readSettingsFromIni, taa.hpp:1198-1339 ----------------------------------
+def _settings_from(values):
+    """The parameter blocks of tests/golden/taa_settings_values.json (the state make_ini_golden.py gave the reference's class)."""
+    params = [abi.TaaParameters(), abi.TaaParameters()]
+    for p, v in zip(params, values["param"]):
+        for k, x in v.items():
+            if k == "mDebugMask":
+                for i in range(4):
+                    p.mDebugMask[i] = x[i]
+            else:
+                setattr(p, k, x)
+    s, pp = abi.taa_invokee_settings(), abi.TaaPostProcessPush()
+    pr = values["primary"]
+    for k in ("mTaaEnabled", "mSplitScreen", "mResetHistoryOnChange", "mPostProcessEnabled", "mSharpener", "mSplitX", "mSharpenFactor"):
+        setattr(s, k, pr[k])
+    for k in ("mSampleDistribution", "mFixedJitterIndex", "mJitterSlowMotion", "mJitterExtraScale", "mJitterRotateDegrees"):
+        setattr(s.jitter, k, pr[k])
+    offs = (C.c_float * (2 * len(pr["mDebugSampleOffsets"])))(*[c for o in pr["mDebugSampleOffsets"] for c in o])
+    s.jitter.mDebugSampleOffsets = C.cast(offs, C.POINTER(C.c_float))
+    s.jitter.mDebugSampleOffsetsCount = len(pr["mDebugSampleOffsets"])
+    s._keep = offs
+    po = values["post"]
+    pp.zoom, pp.showZoomBox = po["zoom"], po["showZoomBox"]
+    for i in range(4):
+        pp.zoomSrcLTWH[i], pp.zoomDstLTWH[i] = po["zoomSrcLTWH"][i], po["zoomDstLTWH"][i]
+    return params, s, pp
+
+
+def _f32(x):
+    return float(np.float32(x))
+
+
+def test_write_settings_ini_matches_the_reference_text(taalib):
+    """Byte for byte what the reference's writeSettingsToIni + mINI generate() wrote for the same values (make_ini_golden.py)."""
+    values = json.load(open(os.path.join(GOLDEN, "taa_settings_values.json")))
+    params, s, pp = _settings_from(values)
+    text = host.write_settings_ini(params, s, pp)
+    want = open(os.path.join(GOLDEN, "taa_settings_written.ini")).read()
+    assert text == want
+
+
+def test_read_settings_ini_matches_the_reference(taalib):
+    """Every field as the reference's readSettingsFromIni left it after reading tests/golden/taa_settings_input.ini (mixed case, comments,
+    empty and missing keys, duplicates, 'true'/'yes', trailing text after numbers, fewer sample offsets than before)."""
+    values = json.load(open(os.path.join(GOLDEN, "taa_settings_values.json")))
+    want = json.load(open(os.path.join(GOLDEN, "taa_settings_read.json")))
+    params, s, pp = _settings_from(values)
+    offs = host.read_settings_ini(open(os.path.join(GOLDEN, "taa_settings_input.ini")).read(), params, s, pp)
+    for p, w in zip(params, want["param"]):
+        for k, x in w.items():
+            if k == "mDebugMask":
+                assert [p.mDebugMask[i] for i in range(4)] == [_f32(c) for c in x], k
+            else:
+                got = getattr(p, k)
+                assert got == (_f32(x) if isinstance(got, float) else x), (k, got, x)
+    pr = want["primary"]
+    for k in ("mTaaEnabled", "mSplitScreen", "mResetHistoryOnChange", "mPostProcessEnabled", "mSharpener", "mSplitX"):
+        assert getattr(s, k) == pr[k], k
+    assert s.mSharpenFactor == _f32(pr["mSharpenFactor"])
+    for k in ("mSampleDistribution", "mFixedJitterIndex", "mJitterSlowMotion"):
+        assert getattr(s.jitter, k) == pr[k], k
+    for k in ("mJitterExtraScale", "mJitterRotateDegrees"):
+        assert getattr(s.jitter, k) == _f32(pr[k]), k
+    assert [(_f32(a), _f32(b)) for a, b in pr["mDebugSampleOffsets"]] == offs
+    po = want["post"]
+    assert (pp.zoom, pp.showZoomBox) == (po["zoom"], po["showZoomBox"])
+    assert [pp.zoomSrcLTWH[i] for i in range(4)] == po["zoomSrcLTWH"] and [pp.zoomDstLTWH[i] for i in range(4)] == po["zoomDstLTWH"]
+
+
+def test_settings_ini_round_trip_and_errors(taalib):
+    values = json.load(open(os.path.join(GOLDEN, "taa_settings_values.json")))
+    params, s, pp = _settings_from(values)
+    text = host.write_settings_ini(params, s, pp)
+    p2 = [abi.TaaParameters(), abi.TaaParameters()]
+    s2, pp2 = abi.taa_invokee_settings(), abi.TaaPostProcessPush()
+    host.read_settings_ini(text, p2, s2, pp2)
+    # std::to_string(float) keeps six decimals: what survives the trip is the written text
+    assert host.write_settings_ini(p2, s2, pp2) == host.write_settings_ini(*_reparse(text))
+    assert p2[1].mInterpolationMode == params[1].mInterpolationMode and p2[0].mUseYCoCg == params[0].mUseYCoCg
+    assert s2.jitter.mDebugSampleOffsetsCount == 3 and pp2.zoomDstLTWH[0] == -3
+    with pytest.raises(host.TaaError) as e:
+        host.read_settings_ini("[TAA_Param_0]\nmAlpha=fast\nmMinAlpha=0.25\n", p2, s2, pp2)
+    assert "malpha" in str(e.value).lower()
+    assert p2[0].mMinAlpha == 0.25  # the valid keys are applied all the same
+    # an empty text changes nothing
+    before = bytes(p2[0])
+    host.read_settings_ini("", p2, s2, pp2)
+    assert bytes(p2[0]) == before
+
+
+def _reparse(text):
+    p = [abi.TaaParameters(), abi.TaaParameters()]
+    s, pp = abi.taa_invokee_settings(), abi.TaaPostProcessPush()
+    host.read_settings_ini(text, p, s, pp)
+    return p, s, pp
