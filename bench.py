@@ -314,7 +314,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5], help="2: 4K resolve (the bench line); 3: config 3 settings; 5: 64 independent 1080p camera streams (BASELINE configs[4])")
     ap.add_argument("--motion", default="pan", choices=["pan", "varying"], help="varying: perturb the synthetic velocity field (kernel-only tuning aid; the bench line is 'pan', SURVEY 8d)")
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
@@ -327,6 +327,9 @@ def main():
             args.steps = 20  # bounded: each step is ~1 s of CPU work
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.config == 5 and args.impl != "reference":
+        from taa_star_b200 import streams
+        return streams.bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX)
     if args.gpus > 1 or world > 1:
         from taa_star_b200 import sharded
         return sharded.bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX)
