@@ -860,10 +860,9 @@ cudaError_t launch_resolve_strip(const ResolveArgs& A, unsigned int* fix_list, u
 	static const int unr = [] { const char* s = getenv("TAA_STRIP_UNROLL"); return s ? atoi(s) : 1; }();
 	const int minb = minb_env ? minb_env : (rej ? 2 : 3);
 #define TAA_STRIP_GO(MB, UN) return launch_minb<MB, UN>(A, fix_list, fix_count, fix_count_next, band, stream)
-	if (minb == 2) { if (unr == 1) TAA_STRIP_GO(2, 1); if (unr == 2) TAA_STRIP_GO(2, 2); TAA_STRIP_GO(2, 4); }
-	if (unr == 1) TAA_STRIP_GO(3, 1);
-	if (unr == 2) TAA_STRIP_GO(3, 2);
-	TAA_STRIP_GO(3, 4);
+	if (minb == 2) { if (unr == 4) TAA_STRIP_GO(2, 4); TAA_STRIP_GO(2, 1); }
+	if (unr == 4) TAA_STRIP_GO(3, 4);
+	TAA_STRIP_GO(3, 1);
 #undef TAA_STRIP_GO
 }
 
