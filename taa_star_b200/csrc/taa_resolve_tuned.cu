@@ -1,4 +1,6 @@
-// taa_resolve_tuned.cu — the tuned resolve kernel for the BASELINE configs 2-5 family of settings
+// taa_resolve_tuned.cu — the 32x32-TILE tuned resolve kernel for the BASELINE configs 2-5 family of settings. Since round r01_d the default
+// is the strip kernel (taa_resolve_strip.cu, same contract, 1.4-1.9x faster); this one is its A/B partner (TAA_TUNED_VARIANT=tile) and
+// the place where the arithmetic contract both share is written down.
 // (SURVEY A.8): YCoCg variance clipping, clipAabb rectification, Catmull-Rom history, velocity
 // reprojection, optional outside / depth / anti-ghost rejection, velocity alpha, Lottes weighting,
 // near-clamp anti-flicker. Everything else runs on the exact generic kernel (taa_dispatch.cu decides).
