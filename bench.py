@@ -323,6 +323,10 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 when the user has not set it; the CPU arm is to use every host thread it can get.
+        # (Set before anything loads an OpenMP runtime: torch and the oracle libraries are imported inside run_reference.)
+        if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         if args.steps > 20:
             args.steps = 20  # bounded: each step is ~1 s of CPU work
         return run_reference(args)

@@ -258,37 +258,43 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
         step(i)
     torch.cuda.synchronize()
     assert sh.poll() == abi.TAA_OK, "halo overflow during warm-up"
-    graphs = None
-    if os.environ.get("TAA_SHARDED_GRAPHS", "1") != "0":  # one CUDA graph per step of the cycle (kernels + NCCL exchange): see capture_step
-        graphs = []
-        launches_c0 = sh.launch_count  # (the contexts count launches as they record them: a replay repeats what the capture recorded)
-        for k in range(2 * NSETS):
-            i = nwarm + 1 + k
+    graphs, cycle_graph, graph_note = None, None, "eager"
+    if os.environ.get("TAA_SHARDED_GRAPHS", "1") != "0":
+        # One CUDA graph per step of the cycle (kernels + NCCL exchange, see capture_steps) and the whole cycle as one graph (no launch gap
+        # between its steps; used wherever a full cycle fits into the timed steps). Capturing does not communicate, replaying does: every
+        # rank captures everything first, the ranks agree that all captures succeeded, and only then is anything replayed.
+        def args_of(i):
             f, fp = frames[i % NSETS], frames[(i - 1) % NSETS]
-            g = sh.capture_step(unis[i % NSETS], f.color, f.depth, f.velocity, L.iy0, history_depth=fp.depth if cfg_id == 3 else None)
-            with torch.cuda.stream(sh.compute):
-                g.replay()  # run it once: device state follows the host-side parities
-            graphs.append(g)
-        torch.cuda.synchronize()
-        assert sh.poll() == abi.TAA_OK
-        launches_per_cycle = sh.launch_count - launches_c0
-        nwarm += 2 * NSETS
-        # ... and the whole cycle as one graph (no launch gap between its steps); used wherever a full cycle fits into the timed steps
-        cyc = []
-        for k in range(2 * NSETS):
-            i = nwarm + 1 + k
-            f, fp = frames[i % NSETS], frames[(i - 1) % NSETS]
-            cyc.append(((unis[i % NSETS], f.color, f.depth, f.velocity, L.iy0), dict(history_depth=fp.depth if cfg_id == 3 else None)))
-        cycle_graph = sh.capture_steps(cyc)
-        with torch.cuda.stream(sh.compute):
-            cycle_graph.replay()
-        torch.cuda.synchronize()
-        assert sh.poll() == abi.TAA_OK
-        nwarm += 2 * NSETS
+            return (unis[i % NSETS], f.color, f.depth, f.velocity, L.iy0), dict(history_depth=fp.depth if cfg_id == 3 else None)
 
-        def step(i, u=None):  # noqa: F811
+        parity0, ok, why = sh.parity, 1, ""
+        launches_c0 = sh.launch_count  # (the contexts count launches as they record them: a replay repeats what the capture recorded)
+        try:
+            gs = [sh.capture_steps([args_of(nwarm + 1 + k)]) for k in range(2 * NSETS)]
+            launches_per_cycle = sh.launch_count - launches_c0
+            cg = sh.capture_steps([args_of(nwarm + 1 + 2 * NSETS + k) for k in range(2 * NSETS)])
+        except Exception as e:  # noqa: BLE001 - any capture failure means: run eagerly
+            ok, why = 0, f"{type(e).__name__}: {str(e)[:120]}"
+            sh.parity = parity0
+            sh._pending = []
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            graphs, cycle_graph = gs, cg
+            graph_note = "CUDA graphs (kernels on 3 streams + the NCCL exchange): one per cycle of 8 steps, single-step graphs for the remainder"
             with torch.cuda.stream(sh.compute):
-                graphs[(i - (nwarm + 1)) % (2 * NSETS)].replay()
+                for g in graphs:
+                    g.replay()  # run them once: the device state follows the host-side parities the captures advanced
+                cycle_graph.replay()
+            torch.cuda.synchronize()
+            assert sh.poll() == abi.TAA_OK
+            nwarm += 4 * NSETS
+
+            def step(i, u=None):  # noqa: F811
+                with torch.cuda.stream(sh.compute):
+                    graphs[(i - (nwarm + 1)) % (2 * NSETS)].replay()
+        else:
+            graph_note = "eager (graph capture failed on some rank" + (f": {why}" if why else "") + ")"
     clocks = ClockSampler(local) if rank == 0 else None
     launches0 = sh.launch_count
     dist.barrier()
@@ -371,7 +377,7 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
             "config": {"workload": f"{W}x{H} TAA resolve sharded in {world} row bands, BASELINE configs[3] (config {cfg_id} settings)",
                        "arithmetic": "exact general kernel" if args.exact else "tuned kernel + exact fix-up pass", "halo_rows": halo,
                        "exchange": "NCCL send/recv of 2 x halo rows of history per neighbour per frame, overlapped with the interior resolve",
-                       "launch": "CUDA graphs (kernels on 3 streams + the NCCL exchange): one per cycle of 8 steps, single-step graphs for the remainder" if graphs is not None else "eager",
+                       "launch": graph_note,
                        "l2": f"inputs larger than L2: {NSETS} frame sets rotated, history ping-pong"},
             "gpu_launches": int(launches.item()),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
