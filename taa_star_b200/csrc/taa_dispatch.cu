@@ -19,19 +19,29 @@ cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, i
 	*launched = 0;
 	if (!(c->desc.flags & TAA_FLAG_EXACT) && tuned_supports(A)) {
 		c->last_was_tuned = true;
-		cudaError_t e = ensure_fix_buffers(c);
-		if (e != cudaSuccess) return e;
-		unsigned int* cnt = c->fix_count + c->fix_parity;
-		unsigned int* cnt_next = c->fix_count + (c->fix_parity ^ 1);
-		c->fix_parity ^= 1;
-		// TAA_TUNED_VARIANT=tile selects the 32x32-tile kernel (A/B aid); both honour the same contract
-		static const bool tile = [] { const char* v = getenv("TAA_TUNED_VARIANT"); return v && v[0] == 't'; }();
-		e = tile ? launch_resolve_tuned(A, c->fix_list, cnt, cnt_next, (c->desc.flags & TAA_FLAG_FIXUP_ALL) != 0, s)
-		         : launch_resolve_strip(A, c->fix_list, cnt, cnt_next, (c->desc.flags & TAA_FLAG_FIXUP_ALL) != 0, s);
+		// The exact fix-up pass has something to decide only if (a) the mask is bound (`rectified`, taa.comp:845, is reported through it
+		// alone), (b) dynamic anti-ghosting is on (the sign of a filtered alpha that cancels to ~0 flips `rejected`, and with it the colour),
+		// or (c) TAA_FLAG_FIXUP_ALL asks for it. Otherwise the tuned kernel runs alone: its colours are within ~1e-5 of the exact ones.
+		const TaaParameters& P = A.ubo.param[0];
+		const bool fixup_all = (c->desc.flags & TAA_FLAG_FIXUP_ALL) != 0;
+		const bool need_fixup = fixup_all || A.mask.p != nullptr || P.mDynamicAntiGhosting;
+		static const bool tile = [] { const char* v = getenv("TAA_TUNED_VARIANT"); return v && v[0] == 't'; }();  // A/B aid: the 32x32-tile kernel
+		unsigned int *list = nullptr, *cnt = nullptr, *cnt_next = nullptr;
+		if (need_fixup) {
+			cudaError_t e = ensure_fix_buffers(c);
+			if (e != cudaSuccess) return e;
+			list = c->fix_list;
+			cnt = c->fix_count + c->fix_parity;
+			cnt_next = c->fix_count + (c->fix_parity ^ 1);
+			c->fix_parity ^= 1;
+		}
+		cudaError_t e = tile ? launch_resolve_tuned(A, list, cnt, cnt_next, fixup_all, s) : launch_resolve_strip(A, list, cnt, cnt_next, fixup_all, s);
 		if (e != cudaSuccess) return e;
 		*launched = 1;
-		e = launch_resolve_fixup(A, c->fix_list, cnt, A.result.p != nullptr, c->num_sms, s);
-		if (e == cudaSuccess) *launched = 2;
+		if (need_fixup) {
+			e = launch_resolve_fixup(A, list, cnt, A.result.p != nullptr, c->num_sms, s);
+			if (e == cudaSuccess) *launched = 2;
+		}
 		return e;
 	}
 	c->last_was_tuned = false;

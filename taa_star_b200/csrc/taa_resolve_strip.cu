@@ -502,7 +502,9 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmemT<RE
 			// any(greaterThan(abs(diff), 0.001)) == (largest component > 0.001): only the largest component can flip the decision
 			const float dmax = fmaxf(dx, fmaxf(dy, dz));
 			rectified = dmax > 0.001f;
-			if (fabsf(dmax - 0.001f) < fix_band) uncertain = true;
+			// (`rectified` is only reported through the mask: without a mask binding there is nothing to decide exactly; the colours of the
+			// two arithmetics agree to ~1e-5 either way)
+			if (A.mask.p != nullptr && fabsf(dmax - 0.001f) < fix_band) uncertain = true;
 		}
 
 		// ---- blend (taa.comp:848-900) ----

@@ -34,7 +34,7 @@ def max_abs_nan_aware(a, b):
     return float(np.nan_to_num(d, nan=np.inf).max())
 
 
-def check_tuned(oracle, u, ins, hist, hist_depth=None, ctx=None, want=("history_out", "result", "mask"), expect_tuned=True):
+def check_tuned(oracle, u, ins, hist, hist_depth=None, ctx=None, want=("history_out", "result", "mask"), expect_tuned=True, expect_launches=None):
     in_h, in_w = ins["depth"].shape
     ref = oracle.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=hist_depth, want=want)
     own = ctx is None
@@ -43,7 +43,9 @@ def check_tuned(oracle, u, ins, hist, hist_depth=None, ctx=None, want=("history_
     n0 = ctx.launch_count
     got = run_gpu_resolve(ctx, u, ins, hist, hist_depth=hist_depth, want=want)
     launches = ctx.launch_count - n0
-    assert launches == (2 if expect_tuned else 1), f"{launches} launches: the {'tuned' if expect_tuned else 'general'} path was expected"
+    if expect_launches is None:
+        expect_launches = 2 if expect_tuned else 1
+    assert launches == expect_launches, f"{launches} launches: the {'tuned' if expect_tuned else 'general'} path ({expect_launches}) was expected"
     fix = ctx.fixup_pixels()
     if own:
         ctx.close()
@@ -352,3 +354,35 @@ def test_tile_kernel_variant_in_a_subprocess():
                         "test_single_frame or test_tiny_and_ragged_sizes or test_extreme_and_non_finite_motion or test_fixup_pass_is_bit_exact"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("cfg,launches", [("config2", 1), ("config3", 2)])
+def test_without_a_mask_binding(oracle, cfg, launches):
+    """`rectified` is reported through the mask alone: without a mask binding the fix-up pass runs only where a rejection predicate can be
+    undecided (dynamic anti-ghosting, config 3); config 2 is the tuned kernel alone. Colours stay within 2^-10 per frame and >= 60 dB
+    free-running, on the uniform-motion path and on the general one."""
+    w, h = 256, 144
+    p = CFG[cfg]()
+    for pan, vary in (((3.0, 0.5), False), ((2.0, -1.5), True)):
+        sc = SyntheticScene(w, h, pan_px=pan)
+        ctx = host.TaaContext((w, h))
+        hist_ref = np.zeros((h, w, 4), np.float16)
+        hist_free = hist_ref.copy()
+        prev_depth = None
+        for n in range(24):
+            f = sc.frame(n)
+            ins = np_inputs(f)
+            if vary:
+                yy, xx = np.meshgrid(np.arange(h, dtype=np.float32), np.arange(w, dtype=np.float32), indexing="ij")
+                vel = ins["velocity"].astype(np.float32)
+                vel[..., 0:2] *= (1.0 + 0.25 * np.sin(xx * 0.11 + n) * np.cos(yy * 0.13))[..., None]
+                ins["velocity"] = vel.astype(np.float16)
+            u = configs.uniforms_for(p, f.jitter_ndc, reset_history=(n == 0))
+            hd = prev_depth if prev_depth is not None else ins["depth"]
+            ref, got, d, _ = check_tuned(oracle, u, ins, hist_ref, hist_depth=hd, ctx=ctx, want=("history_out", "result"), expect_launches=launches)
+            free = run_gpu_resolve(ctx, u, ins, hist_free, hist_depth=hd, want=("history_out", "result"))
+            hist_ref, hist_free = ref["history_out"], free["history_out"]
+            prev_depth = ins["depth"]
+        q = psnr(ref["result"][..., :3], free["result"][..., :3])
+        assert q >= PSNR_MIN, f"PSNR after 24 free-running frames: {q:.1f} dB"
+        ctx.close()
