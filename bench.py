@@ -298,7 +298,7 @@ def run_single(args):
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                      "traffic_source": traffic_src, "algorithmic_bytes": BYTES_PER_PX[cfg_id] * px,
                      "peak_source": peak_src, "bytes_per_px": BYTES_PER_PX[cfg_id],
-                     "kernel": "taa_resolve_strip_kernel + taa_resolve_fixup_kernel (one step)" if not args.exact else "taa_resolve_generic_kernel"},
+                     "kernel": (json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"config{cfg_id}", {}).get("kernel", "taa_resolve_strip_kernel")) if not args.exact else "taa_resolve_generic_kernel"},
         "cpu_baseline": {"value": round(cpu_mpx, 3), "unit": "Mpixels/s", "cores": cores, "kind": cpu_kind, "sample": sample},
         "e2e": {"value": round(e2e_mpx, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "fps": round(e2e_steps / e2e_dt, 1), "path": "taa_invokee_frame_host: pinned host G-buffer -> H2D -> render() -> D2H of the final image, 3 frames in flight",
