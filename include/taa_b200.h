@@ -221,7 +221,10 @@ enum {
 	 *        reprojection; BASELINE configs 2-5) run on the shared-memory tiled kernel: coordinates and every
 	 *        rejection predicate are evaluated exactly, colour filtering is re-associated and contracted (within
 	 *        ~1e-5 of the exact result, gate 2^-10), and the pixels whose `rectified` predicate sits near its
-	 *        threshold are recomputed exactly by a second small launch, so integer masks are bit-exact.
+	 *        threshold (or whose filtered history alpha cancels to ~0 under dynamic anti-ghosting) are recomputed
+	 *        exactly by a second small launch, so integer masks are bit-exact. That second launch happens only when
+	 *        it has something to decide: `mask` is bound (`rectified` is reported through it alone) or
+	 *        mDynamicAntiGhosting is on (an undecided `rejected` changes the colour).
 	 *        Every other settings block runs on the exact general kernel.
 	 * EXACT: always the general kernel: every fp32 operation in the order of the reference shader with IEEE
 	 *        round-to-nearest and no contraction; all outputs bit-identical to oracle/ on finite inputs. */
