@@ -194,7 +194,9 @@ __device__ __forceinline__ void load_win0(Win0<REJ>& w, const unsigned char* p, 
 // FAST = the tile's motion is uniform (every staged velocity texel bit-identical, no mover near, all footprints interior, footprint
 // rows advancing one per pixel row): history coordinates and Catmull-Rom weights come from the per-row / per-column tables, and the
 // window never restarts. The arithmetic is the very same as in the general path (same functions of the same inputs).
-template <bool REJ, bool ALPHA, bool FAST, int UNR>
+// DIAG = the call reports something beyond the colours: the mask is bound or a fix-up list is kept. Without it the `rectified` bookkeeping
+// (taa.comp:845 feeds the mask and the debug views only) is not evaluated at all.
+template <bool REJ, bool ALPHA, bool FAST, bool DIAG, int UNR>
 __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmemT<REJ>& sm, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
                                              const float fix_band, const int x0, const int y0, const int rows_valid, const int warp, const int lane,
                                              const Win0<REJ>& w0) {
@@ -453,7 +455,7 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmemT<RE
 		}
 
 		// ---- rejection (taa.comp:787-823), exact predicates ----
-		bool rejected = false, uncertain = fix_band > 3.0e38f;  // TAA_FLAG_FIXUP_ALL
+		bool rejected = false, uncertain = DIAG && fix_band > 3.0e38f;  // TAA_FLAG_FIXUP_ALL
 		bool check_ring = false;
 		float writeDynamicMask = 0.f;
 		if (REJ) {
@@ -498,13 +500,15 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmemT<RE
 		if (ma > 1.0f) {
 			const float s = rcp_approx(ma);
 			hc = make_float3(fmaf(vcl.x, s, mean.x), fmaf(vcl.y, s, mean.y), fmaf(vcl.z, s, mean.z));
-			const float dx = fabsf(hc.x - hist.x), dy = fabsf(hc.y - hist.y), dz = fabsf(hc.z - hist.z);
-			// any(greaterThan(abs(diff), 0.001)) == (largest component > 0.001): only the largest component can flip the decision
-			const float dmax = fmaxf(dx, fmaxf(dy, dz));
-			rectified = dmax > 0.001f;
-			// (`rectified` is only reported through the mask: without a mask binding there is nothing to decide exactly; the colours of the
-			// two arithmetics agree to ~1e-5 either way)
-			if (A.mask.p != nullptr && fabsf(dmax - 0.001f) < fix_band) uncertain = true;
+			if (DIAG) {
+				const float dx = fabsf(hc.x - hist.x), dy = fabsf(hc.y - hist.y), dz = fabsf(hc.z - hist.z);
+				// any(greaterThan(abs(diff), 0.001)) == (largest component > 0.001): only the largest component can flip the decision
+				const float dmax = fmaxf(dx, fmaxf(dy, dz));
+				rectified = dmax > 0.001f;
+				// (`rectified` is only reported through the mask: without a mask binding there is nothing to decide exactly; the colours of the
+				// two arithmetics agree to ~1e-5 either way)
+				if (A.mask.p != nullptr && fabsf(dmax - 0.001f) < fix_band) uncertain = true;
+			}
 		}
 
 		// ---- blend (taa.comp:848-900) ----
@@ -541,7 +545,7 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmemT<RE
 			const __half2 bm = __floats2half2_rn(outb, writeDynamicMask), b1 = __floats2half2_rn(outb, 1.0f);
 			*reinterpret_cast<uint2*>(A.history_out.p + o_hist) = make_uint2(*reinterpret_cast<const unsigned int*>(&rg), *reinterpret_cast<const unsigned int*>(&bm));
 			if (A.result.p) *reinterpret_cast<uint2*>(A.result.p + o_res) = make_uint2(*reinterpret_cast<const unsigned int*>(&rg), *reinterpret_cast<const unsigned int*>(&b1));
-			if (A.mask.p) *reinterpret_cast<unsigned int*>(A.mask.p + o_mask) = (rejected ? 1u : 0u) | (rectified ? 2u : 0u) | (2u << 2);
+			if (DIAG && A.mask.p) *reinterpret_cast<unsigned int*>(A.mask.p + o_mask) = (rejected ? 1u : 0u) | (rectified ? 2u : 0u) | (2u << 2);
 		}
 		o_hist += (unsigned int)A.history_out.pitch;
 		o_res += (unsigned int)A.result.pitch;
@@ -559,11 +563,11 @@ __device__ __forceinline__ void strip_phase2(const ResolveArgs& A, StripSmemT<RE
 		} else {
 			f_hd = f_hd_next;
 		}
-		if (uncertain && xvalid) fixbits |= 1u << rr;
+		if (DIAG && uncertain && xvalid) fixbits |= 1u << rr;
 	}
 
 	// ---- hand the undecidable pixels of the strip to the exact pass (one atomic per warp) ----
-	if (fix_list != nullptr && __ballot_sync(0xffffffffu, fixbits != 0u)) {
+	if (DIAG && fix_list != nullptr && __ballot_sync(0xffffffffu, fixbits != 0u)) {
 		const int n = __popc(fixbits);
 		int pre = n;
 #pragma unroll
@@ -598,7 +602,7 @@ __device__ __forceinline__ void stage_depth(const Img& im, float (*dst)[TW], int
 	}
 }
 
-template <bool REJ, bool ALPHA, int MINB, int UNR>
+template <bool REJ, bool ALPHA, bool DIAG, int MINB, int UNR>
 __global__ void __launch_bounds__(NT, MINB)
 taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
                          unsigned int* __restrict__ fix_count_next, const float fix_band, const bool use_bulk) {
@@ -807,14 +811,14 @@ taa_resolve_strip_kernel(const __grid_constant__ ResolveArgs A, unsigned int* __
 		asm volatile("" : "+r"(w0.t[0]), "+r"(w0.t[1]), "+r"(w0.t[2]), "+r"(w0.t[3]), "+r"(w0.t[4]), "+r"(w0.t[5]));
 	}
 
-	if (fast) strip_phase2<REJ, ALPHA, true, UNR>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane, w0);
-	else strip_phase2<REJ, ALPHA, false, UNR>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane, w0);
+	if (fast) strip_phase2<REJ, ALPHA, true, DIAG, UNR>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane, w0);
+	else strip_phase2<REJ, ALPHA, false, DIAG, UNR>(A, sm, fix_list, fix_count, fix_band, x0, y0, rows_valid, warp, lane, w0);
 }
 
-template <bool REJ, bool ALPHA, int MINB, int UNR>
+template <bool REJ, bool ALPHA, bool DIAG, int MINB, int UNR>
 cudaError_t launch_variant(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, float band, cudaStream_t stream) {
 	using StripSmem = StripSmemT<REJ>;
-	auto kern = taa_resolve_strip_kernel<REJ, ALPHA, MINB, UNR>;
+	auto kern = taa_resolve_strip_kernel<REJ, ALPHA, DIAG, MINB, UNR>;
 	static bool configured = false;  // per variant
 	if (!configured) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StripSmem));
@@ -843,10 +847,13 @@ cudaError_t launch_minb(const ResolveArgs& A, unsigned int* fix_list, unsigned i
 	const TaaParameters& P = A.ubo.param[0];
 	const bool rej = P.mDepthCulling || P.mRejectOutside || P.mDynamicAntiGhosting;
 	const bool alp = P.mVelBasedAlpha || P.mLumaWeightingLottes || P.mReduceBlendNearClamp;
-	if (rej) return alp ? launch_variant<true, true, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream)
-	                    : launch_variant<true, false, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream);
-	return alp ? launch_variant<false, true, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream)
-	           : launch_variant<false, false, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream);
+	const bool diag = fix_list != nullptr || A.mask.p != nullptr;  // (the rejection variants are built with DIAG only)
+	if (rej) return alp ? launch_variant<true, true, true, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream)
+	                    : launch_variant<true, false, true, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream);
+	if (diag) return alp ? launch_variant<false, true, true, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream)
+	                     : launch_variant<false, false, true, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream);
+	return alp ? launch_variant<false, true, false, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream)
+	           : launch_variant<false, false, false, MINB, UNR>(A, fix_list, fix_count, fix_count_next, band, stream);
 }
 
 }  // namespace
