@@ -6,7 +6,7 @@
 // instructions per pixel, and behind that stalled on the latency of first-touch loads):
 //   * one CTA = 64 x 32 output pixels, 8 warps laid out 2 x 4; a thread walks down 8 rows of one column, so the per-strip
 //     set-up (history window start, first row sums, pointers) is paid once per 8 pixels;
-//   * the raw colour tile (36 x 68 texels, 2-texel halo) and the raw velocity tile (34 x 68) are staged into shared memory with
+//   * the raw colour and velocity tiles (36 x 68 texels each, 2-texel halo; plus the 32 x 64 depth tile of the rejection variants) are staged into shared memory with
 //     cp.async — every first-touch DRAM access of the CTA is in flight at once, none goes through registers, and the coordinate
 //     tables are built while they arrive. Phase 1 then samples the colour tile out of shared memory (in place: the sampled
 //     YCoCg tile overwrites the raw one) and the per-pixel velocity footprint is four LDS instead of four global loads;
@@ -17,7 +17,13 @@
 //     window: two extra 4-byte loads per row instead of 20 per pixel;
 //   * uniform velocity footprints (all four texels bit-identical and finite: lerp(p, p, w) == p exactly) skip the bilinear arithmetic;
 //   * the sampler's sub-texel bleed of the colour taps is applied with mixed-precision FMAs (fma.rn.f32.f16: f16 x f16 + f32);
-//   * the pixels handed to the exact pass are collected per strip and appended with one atomic per warp.
+//   * warps whose tile has UNIFORM motion (every staged velocity texel bit-identical and finite, no mover within two texels; per warp:
+//     all history footprints interior and advancing one row per pixel row) take a path (FAST) in which history coordinates and
+//     Catmull-Rom weights come from per-row / per-column tables built once per tile — the very same functions of the same inputs, so the
+//     results are bit-identical to the general path — and the window never restarts;
+//   * the pixels handed to the exact pass are collected per strip and appended with one atomic per warp; without a mask binding and
+//     without a fix-up list (DIAG = false) the `rectified` bookkeeping is not evaluated at all.
+// Measured history of these choices: DESIGN.md section 5 ("What the profiles say").
 #include "taa_tuned_common.cuh"
 #include "taa_kernels.h"
 #include <cstdlib>
