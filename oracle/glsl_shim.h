@@ -1,6 +1,6 @@
 /*
  * glsl_shim.h — just enough GLSL 4.60 compute semantics in C++17 to compile the REFERENCE's own shader sources
- * (shaders/taa.comp, sharpen.comp, post_process.comp, antialias_fxaa_prepare.comp, antialias_fxaa.comp + Fxaa3_11_mod.h, read where they lie under /root/reference by
+ * (shaders/taa.comp, sharpen.comp, sharpen_cas.comp + ffx_cas.h + the used part of ffx_a.h, post_process.comp, antialias_fxaa_prepare.comp, antialias_fxaa.comp + Fxaa3_11_mod.h, read where they lie under /root/reference by
  * oracle/ref_build.py) into oracle/_ref/libtaa_ref.so. TEST INFRASTRUCTURE, like everything under oracle/.
  *
  * This file holds no algorithm of the reference: it is the "GLSL machine" (vector types, built-ins, the sampler
@@ -13,7 +13,9 @@
  * ref_build.py rewrites the shader text mechanically: comments stripped, `layout(...)` resource declarations turned
  * into thread_local globals, in/out/inout parameters into values/references, floating literals suffixed with f,
  * multi-component swizzles `.rgb` into `._rgb()`, `bool` inside interface blocks into the 4-byte bool32, `main`
- * renamed. Nothing else of the source is touched.
+ * renamed. Nothing else of the source is touched. sharpen_cas.comp: of its include ffx_a.h (AMD's ~1900-line portability header) only the
+ * type macros and the functions the shader uses are spliced in by name, of ffx_cas.h the non-packed GPU section; its imageLoad calls (float
+ * image) become imageLoadF; members of its instance-less push-constant block become globals.
  */
 #pragma once
 #include <cmath>
@@ -46,6 +48,7 @@ struct vec2 {
 	template <class A> explicit vec2(A a) : x((float)a), y((float)a) {}
 	template <class A, class B> vec2(A a, B b) : x((float)a), y((float)b) {}
 	vec2(const ivec2& v);  // GLSL implicit int -> float conversion
+	explicit vec2(const uvec2& v);
 	vec2(const vec2& o) : x(o.x), y(o.y) {}
 	vec2& operator=(const vec2& o) { x = o.x; y = o.y; return *this; }
 	vec2 _xy() const { return vec2(x, y); }
@@ -116,20 +119,30 @@ struct ivec4 {
 	ivec2 _xy() const { return ivec2(x, y); }
 	ivec2 _zw() const { return ivec2(z, w); }
 };
-struct uvec2 { uint x, y; };
+struct uvec2 {
+	uint x, y;
+	uvec2() : x(0), y(0) {}
+	uvec2(uint a, uint b) : x(a), y(b) {}
+};
 struct uvec3 {
 	uint x, y, z;
-	uvec2 _xy() const { return uvec2{x, y}; }
+	uvec3() : x(0), y(0), z(0) {}
+	uvec3(uint a, uint b, uint c) : x(a), y(b), z(c) {}
+	uvec2 _xy() const { return uvec2(x, y); }
 };
 struct uvec4 {
 	union { uint x, r; };
 	uint y, z, w;
 	uvec4() : x(0), y(0), z(0), w(0) {}
 	uvec4(uint a, uint b, uint c, uint d) : x(a), y(b), z(c), w(d) {}
+	uvec2 _xy() const { return uvec2(x, y); }
+	uvec2 _zw() const { return uvec2(z, w); }
 };
 struct bvec2 { bool x, y; };
 struct bvec3 { bool x, y, z; };
 inline vec2::vec2(const ivec2& v) : x((float)v.x), y((float)v.y) {}
+inline vec2::vec2(const uvec2& v) : x((float)v.x), y((float)v.y) {}
+inline uvec2 operator+(const uvec2& a, const uvec2& b) { return uvec2(a.x + b.x, a.y + b.y); }
 inline ivec2::ivec2(const uvec2& v) : x((int)v.x), y((int)v.y) {}
 
 // every operator is one fp32 operation per component
@@ -219,6 +232,17 @@ inline bool all(const bvec2& v) { return v.x && v.y; }
 // mat4: column-major; M * v accumulates column by column, ((M0 v.x + M1 v.y) + M2 v.z) + M3 v.w
 struct mat4 { vec4 c[4]; };
 inline vec4 operator*(const mat4& m, const vec4& v) { return ((m.c[0] * v.x + m.c[1] * v.y) + m.c[2] * v.z) + m.c[3] * v.w; }
+
+// bit casts and bit-field built-ins (GLSL 4.60 8.3, 8.8)
+inline float uintBitsToFloat(uint v) { float f; memcpy(&f, &v, 4); return f; }
+inline uint floatBitsToUint(float f) { uint v; memcpy(&v, &f, 4); return v; }
+inline vec2 uintBitsToFloat(const uvec2& v) { return vec2(uintBitsToFloat(v.x), uintBitsToFloat(v.y)); }
+inline uint bitfieldExtract(uint value, int offset, int bits) { return bits == 0 ? 0u : (bits >= 32 ? value >> offset : (value >> offset) & ((1u << bits) - 1u)); }
+inline uint bitfieldInsert(uint base, uint insert, int offset, int bits) {
+	if (bits == 0) return base;
+	const uint mask = (bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u)) << offset;
+	return (base & ~mask) | ((insert << offset) & mask);
+}
 
 // ---- fp16 -------------------------------------------------------------------------------------------------
 inline float half_to_float(uint16_t h) {
@@ -337,6 +361,11 @@ inline uvec4 imageLoad(const Image& t, const ivec2& c) {
 	return uvec4(((const uint32_t*)(t.data + (long long)c.y * t.pitch))[c.x], 0, 0, 0);
 }
 
+// imageLoad on a float image (sharpen_cas.comp; ref_build.py renames the call): out of range -> 0, like texelFetch
+inline vec4 imageLoadF(const Image& t, const ivec2& c) { return texelFetch(t, c, 0); }
+
 static thread_local uvec3 gl_GlobalInvocationID;
+static thread_local uvec3 gl_LocalInvocationID;
+static thread_local uvec3 gl_WorkGroupID;
 
 }  // namespace glsl

@@ -74,6 +74,8 @@ def ref_lib() -> C.CDLL:
         L.taa_ref_resolve.argtypes = [P(abi.taa_resolve_images), P(abi.TaaUniforms)] + [C.c_int] * 7
         L.taa_ref_sharpen.restype = C.c_int
         L.taa_ref_sharpen.argtypes = [P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int, C.c_float]
+        L.taa_ref_sharpen_cas.restype = C.c_int
+        L.taa_ref_sharpen_cas.argtypes = [P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int, P(abi.TaaCasPush)]
         L.taa_ref_post_process.restype = C.c_int
         L.taa_ref_post_process.argtypes = [P(abi.taa_image), P(abi.taa_image), P(abi.taa_image), C.c_int, C.c_int, P(abi.TaaPostProcessPush)]
         L.taa_ref_fxaa_prepare.restype = C.c_int
@@ -128,6 +130,18 @@ def ref_sharpen(src, factor):
     dst = np.zeros_like(src)
     a, b = _img(src), _img(dst)
     assert ref_lib().taa_ref_sharpen(C.byref(a), C.byref(b), w, h, factor) == 0
+    return dst
+
+
+def ref_cas(src, const0, const1):
+    """sharpen_cas.comp (+ ffx_cas.h's CasFilter) of the reference itself, compiled through the GLSL shim."""
+    h, w = src.shape[:2]
+    dst = np.zeros_like(src)
+    a, b = _img(src), _img(dst)
+    pc = abi.TaaCasPush()
+    for i in range(4):
+        pc.const0[i], pc.const1[i] = const0[i], const1[i]
+    assert ref_lib().taa_ref_sharpen_cas(C.byref(a), C.byref(b), w, h, C.byref(pc)) == 0
     return dst
 
 

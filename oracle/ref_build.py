@@ -46,9 +46,46 @@ def splice_includes(src: str, folder: str) -> str:
     return re.sub(r'^[ \t]*#include\s+"([^"]+)"[^\n]*$', sub, src, flags=re.M)
 
 
+# ---- sharpen_cas.comp: its two includes are AMD's portability header ffx_a.h (every GLSL/HLSL/CPU type and intrinsic wrapper it has:
+# ~1900 lines, most of them needing built-ins the shim does not have) and ffx_cas.h. What the shader USES of ffx_a.h is spliced in by
+# name, read from the reference's file at build time; of ffx_cas.h, the non-packed GPU section (the CPU-side CasSetup and the fp16
+# variant in the same file are not part of this shader's code path).
+FFX_A_DEFINES = re.compile(r"^\s*#define\s+(A[PFU][1-4]|ASU[1-4]|AF[1-4]_AU[1-4]\(x\)|AU[1-4]_AF[1-4]\(x\)|AF[1-4]_\(a\)|AU[1-4]_\(a\))\s")
+FFX_A_GLSL_FUNCS = re.compile(r"^\s*A[FU][1-4]\s+(AF[1-4]_x|AU[1-4]_x|AMax3F1|AMin3F1|ARcpF1|ASatF1|ABfe|ABfiM)\(")
+FFX_A_COMMON_FUNCS = re.compile(r"^\s*A[FU][1-4]\s+(APrxLoSqrtF1|APrxLoRcpF1|APrxMedRcpF1|ARmp8x8)\(")
+
+
+def ffx_a_subset(path: str) -> str:
+    lines = strip_comments(open(path).read()).split("\n")
+    a = next(i for i, l in enumerate(lines) if re.match(r"^#if defined\(A_GLSL\) && defined\(A_GPU\)", l))
+    b = next(i for i, l in enumerate(lines) if re.match(r"^#if defined\(A_HLSL\) && defined\(A_GPU\)", l))
+    out = [l for l in lines[a:b] if FFX_A_DEFINES.match(l) or FFX_A_GLSL_FUNCS.match(l)]
+    out += [l for l in lines[b:] if FFX_A_COMMON_FUNCS.match(l)]
+    return "\n".join(out)
+
+
+def ffx_cas_gpu_section(path: str) -> str:
+    raw = open(path).read()
+    start = raw.index("#ifdef A_GPU", raw.index("NON-PACKED VERSION"))
+    end = raw.index("#if defined(A_GPU) && defined(A_HALF)")
+    return strip_comments(raw[start:end])
+
+
+def cas_source(path: str) -> str:
+    folder = os.path.dirname(path)
+    src = strip_comments(open(path).read())
+    src = re.sub(r'^[ \t]*#include\s+"ffx_a.h"[^\n]*$', lambda m: ffx_a_subset(os.path.join(folder, "ffx_a.h")), src, flags=re.M)
+    src = re.sub(r'^[ \t]*#include\s+"ffx_cas.h"[^\n]*$', lambda m: ffx_cas_gpu_section(os.path.join(folder, "ffx_cas.h")), src, flags=re.M)
+    # the shader's only imageLoad calls read the rgba16f source: the shim's imageLoad is the r32ui one (taa.comp's seg-mask), imageLoadF the float one
+    return src.replace("imageLoad(", "imageLoadF(")
+
+
 def transpile(path: str, ns: str, prelude: str = ""):
     """Returns (C++ text of the shader inside namespace glsl::<ns>, names of globals that carry an initialiser)."""
-    src = splice_includes(strip_comments(open(path).read()), os.path.dirname(path))
+    if os.path.basename(path) == "sharpen_cas.comp":
+        src = cas_source(path)
+    else:
+        src = splice_includes(strip_comments(open(path).read()), os.path.dirname(path))
     out, resets = [], []
     in_block = None   # (kind, name) while inside a struct / uniform block
     depth = 0
@@ -66,6 +103,7 @@ def transpile(path: str, ns: str, prelude: str = ""):
         m = BLOCK_OPEN.match(st)
         if m:  # uniform block (UBO or push constants): a struct plus one thread_local instance, declared at the closing brace
             in_block = ("uniform", m.group(2))
+            block_start = len(out)
             out.append(f"struct {m.group(2)} {{")
             continue
         if in_block is None and re.match(r"^struct\s+\w+\s*\{\s*$", st):
@@ -75,9 +113,15 @@ def transpile(path: str, ns: str, prelude: str = ""):
         if in_block is not None:
             mm = re.match(r"^\}\s*(\w+)?\s*;\s*$", st)
             if mm:
-                out.append("};")
-                if in_block[0] == "uniform":
-                    out.append(f"static thread_local {in_block[1]} {mm.group(1)};")
+                if in_block[0] == "uniform" and mm.group(1) is None:
+                    # a block without an instance name: its members are globals of the shader (function parameters may shadow them)
+                    members = [l.strip() for l in out[block_start + 1:] if l.strip()]
+                    del out[block_start:]
+                    out += [f"static thread_local {l}" for l in members]
+                else:
+                    out.append("};")
+                    if in_block[0] == "uniform":
+                        out.append(f"static thread_local {in_block[1]} {mm.group(1)};")
                 in_block = None
             else:
                 out.append(re.sub(r"\bbool\b", "bool32", line))  # std140: bool is 4 bytes
@@ -268,8 +312,40 @@ extern "C" __attribute__((visibility("default"))) int FXAA_ENTRY(const taa_image
 }
 '''
 
+# sharpen_cas.comp: 64 threads per workgroup, each writes 4 pixels of a 16x16 block (sharpen_cas.comp:30-52); dispatched as
+# ((w + 15) / 16, (h + 15) / 16) workgroups (taa.hpp:1134)
+HARNESS_CAS = r'''
+static void run(const taa_image* src, const taa_image* dst, int w, int h, const TaaCasPush* pc) {
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+	{
+		imgSrc = mk(*src, w, h, F_RGBA16F);
+		imgDst = mk(*dst, w, h, F_RGBA16F);
+		const0 = uvec4(pc->const0[0], pc->const0[1], pc->const0[2], pc->const0[3]);
+		const1 = uvec4(pc->const1[0], pc->const1[1], pc->const1[2], pc->const1[3]);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+		for (int gy = 0; gy < (h + 15) / 16; ++gy)
+			for (int gx = 0; gx < (w + 15) / 16; ++gx)
+				for (int l = 0; l < 64; ++l) {
+					gl_WorkGroupID = uvec3{(uint)gx, (uint)gy, 0u};
+					gl_LocalInvocationID = uvec3{(uint)l, 0u, 0u};
+					shader_main();
+				}
+	}
+}
+}}
+extern "C" __attribute__((visibility("default"))) int taa_ref_sharpen_cas(const taa_image* src, const taa_image* dst, int w, int h, const TaaCasPush* pc) {
+	glsl::ref_cas::run(src, dst, w, h, pc);
+	return 0;
+}
+'''
+
 # (shader, namespace, harness, text put in front of the namespace)
-SHADERS = [("taa.comp", "ref_taa", HARNESS_TAA, ""), ("sharpen.comp", "ref_sharpen", HARNESS_SHARPEN, ""), ("post_process.comp", "ref_post", HARNESS_POST, ""),
+SHADERS = [("taa.comp", "ref_taa", HARNESS_TAA, ""), ("sharpen.comp", "ref_sharpen", HARNESS_SHARPEN, ""), ("sharpen_cas.comp", "ref_cas", HARNESS_CAS, ""),
+           ("post_process.comp", "ref_post", HARNESS_POST, ""),
            ("antialias_fxaa_prepare.comp", "ref_fxaa_prepare", HARNESS_FXAA_PREPARE, ""),
            ("antialias_fxaa.comp", "ref_fxaa_gather", HARNESS_FXAA, "#define GL_ARB_gpu_shader5 1\n#define FXAA_ENTRY taa_ref_fxaa_gather4\n#define FXAA_NS ref_fxaa_gather\n"),
            ("antialias_fxaa.comp", "ref_fxaa_offset", HARNESS_FXAA, "#define FXAA_ENTRY taa_ref_fxaa_offset\n#define FXAA_NS ref_fxaa_offset\n")]

@@ -159,6 +159,25 @@ def test_sharpen_and_post_process():
         assert mismatch_report(f"post_process {c}", oracle_py.ref_post_process(src, dbg, pc), oracle_py.post_process(src, dbg, pc)) is None
 
 
+def test_cas_filter_body():
+    """sharpen_cas.comp + ffx_cas.h's CasFilter (the reference's own text through the shim, with the functions of ffx_a.h it uses spliced in
+    by name) against the hand restatement in taa_oracle.cpp: rgb bit for bit, for every sharpness, on ragged sizes (the 16x16 workgroup
+    tiling hangs over the image; border loads go out of range), on values above 1 and on flat, zero and negative regions.
+    Alpha: the shader stores an uninitialised `AF4 c` (undefined in GLSL); the restatement and the CUDA kernel write 1."""
+    rng = np.random.default_rng(31)
+    for (h, w, sharp) in [(72, 128, 0.5), (37, 53, 0.0), (16, 16, 1.0), (90, 160, 0.8), (1, 1, 0.5), (5, 300, 0.25)]:
+        src = random_history(h, w, 40 + h, alpha_binary=False).astype(np.float32)
+        src[: h // 3, : w // 3, :3] *= 3.0                      # above 1: the filter saturates
+        src[h // 2:, w // 2:, :3] = 0.25                        # flat
+        src[: h // 4, w // 2:, :3] = 0.0                        # zero: the reciprocal approximations see 0
+        src[h // 2:, : w // 4, :3] -= 0.5                       # negative values
+        src[..., :3] += (rng.random((h, w, 3), dtype=np.float32) < 0.02) * 8.0   # isolated peaks
+        src = src.astype(np.float16)
+        c0, c1 = oracle_py.cas_setup(sharp, w, h)
+        a, b = oracle_py.cas(src, c0, c1), oracle_py.ref_cas(src, c0, c1)
+        assert mismatch_report(f"cas {w}x{h} sharpness {sharp}", b[..., :3], a[..., :3]) is None
+
+
 def fxaa_test_image(h, w, seed):
     """Hard edges at all orientations (long ones too, so that the end-of-edge search runs out its steps), thin lines, noise, flat areas."""
     rng = np.random.default_rng(seed)
