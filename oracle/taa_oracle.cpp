@@ -19,7 +19,8 @@
  * GLSL and neither glslang nor a Vulkan ICD exists in the build container. The pins are:
  *   (1) oracle/_ref: the reference's own shader sources, mechanically rewritten to C++ at build time
  *       and compiled against the GLM the reference vendors (oracle/ref_build.py + oracle/glsl_shim.h, oracle/Makefile).
- *       tests/test_oracle_vs_ref.py compares this file against it bit for bit.
+ *       tests/test_oracle_vs_ref.py compares this file against it bit for bit: taa.comp, sharpen.comp, sharpen_cas.comp + ffx_cas.h's
+ *       CasFilter, post_process.comp, antialias_fxaa_prepare.comp, antialias_fxaa.comp + Fxaa3_11_mod.h.
  *   (2) known answers derived from reference code that compiles as-is: CasSetup (ffx_cas.h under A_CPU)
  *       and halton_2_3<8> (tests/golden/known_answers.json, made by tests/golden/make_known_answers.py).
  *
