@@ -207,3 +207,53 @@ def _reparse(text):
     s, pp = abi.taa_invokee_settings(), abi.TaaPostProcessPush()
     host.read_settings_ini(text, p, s, pp)
     return p, s, pp
+
+
+# ---- jitter patterns and the jittered projection against the reference's own code ------------------------------------------------
+def _bits(x):
+    return int(np.float32(x).view(np.uint32))
+
+
+def _from_bits(u):
+    return float(np.uint32(u).view(np.float32))
+
+
+def test_jitter_and_projection_match_the_reference_bit_for_bit(taalib, oracle):
+    """tests/golden/jitter_golden.json: taa<CF>::get_jitter_offset_for_frame for all six distributions x {slow motion, fixed index,
+    rotation, extra scale} x 20 frames x four resolutions, and get_jittered_projection_matrix, produced by the reference's own function
+    bodies compiled as-is (make_jitter_golden.py). The library and the oracle must reproduce every float bit."""
+    g = json.load(open(os.path.join(GOLDEN, "jitter_golden.json")))
+    dbg = [tuple(o) for o in g["debug_offsets"]]
+    checked = 0
+    for res in g["resolutions"]:
+        w, h = res["w"], res["h"]
+        for c in res["cases"]:
+            scale, rot = _from_bits(c["scale"]), _from_bits(c["rot"])
+            for f in range(20):
+                want = (c["xy"][2 * f], c["xy"][2 * f + 1])
+                (x, y), n = host.jitter_offset_for_frame(f, w, h, c["dist"], c["fixed"], scale, c["slow"], rot, dbg)
+                assert n == c["n"], (w, h, c, n)
+                assert (_bits(x), _bits(y)) == want, f"library: {w}x{h} dist {c['dist']} fixed {c['fixed']} slow {c['slow']} scale {scale} rot {rot} frame {f}"
+                (ox, oy), on = oracle.jitter(f, w, h, c["dist"], c["fixed"], scale, c["slow"], rot, dbg)
+                assert on == c["n"]
+                assert (_bits(ox), _bits(oy)) == want, f"oracle: {w}x{h} dist {c['dist']} frame {f}"
+                checked += 1
+        for p in res["proj"]:
+            out = (C.c_float * 16)()
+            taalib.taa_jittered_projection((C.c_float * 16)(*[_from_bits(u) for u in p["in"]]), _from_bits(p["off"][0]), _from_bits(p["off"][1]), out)
+            assert [_bits(v) for v in out] == p["out"], f"projection {w}x{h} frame {p['frame']}"
+            (jx, jy), _ = host.jitter_offset_for_frame(p["frame"], w, h, 2)
+            assert (_bits(jx), _bits(jy)) == tuple(p["off"])
+    assert checked == 4 * 24 * 20
+
+
+def test_reprojection_matrices_match_glm_bit_for_bit(taalib):
+    """taa.hpp:993-994 — glm::inverse(P_cur * V_cur) and P_prev * V_prev — computed with the GLM the reference vendors for twelve camera
+    poses (tests/golden/make_matrix_golden.py); taa_reprojection_matrices must reproduce every float bit."""
+    g = json.load(open(os.path.join(GOLDEN, "matrix_golden.json")))
+    for i, c in enumerate(g):
+        m = {k: (C.c_float * 16)(*[_from_bits(u) for u in c[k]]) for k in ("proj_cur", "view_cur", "proj_prev", "view_prev")}
+        inv, hist = (C.c_float * 16)(), (C.c_float * 16)()
+        assert taalib.taa_reprojection_matrices(m["proj_cur"], m["view_cur"], m["proj_prev"], m["view_prev"], inv, hist) == 0
+        assert [_bits(v) for v in hist] == c["history_view_proj"], f"pose {i}: P_prev * V_prev"
+        assert [_bits(v) for v in inv] == c["inverse_view_proj"], f"pose {i}: inverse(P_cur * V_cur)"
