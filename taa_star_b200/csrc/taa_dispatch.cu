@@ -35,7 +35,9 @@ cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, i
 			cnt_next = c->fix_count + (c->fix_parity ^ 1);
 			c->fix_parity ^= 1;
 		}
-		cudaError_t e = tile ? launch_resolve_tuned(A, list, cnt, cnt_next, fixup_all, s) : launch_resolve_strip(A, list, cnt, cnt_next, fixup_all, s);
+		cudaError_t e = tile ? launch_resolve_tuned(A, list, cnt, cnt_next, fixup_all, s)
+		                     : stream_supports(A) ? launch_resolve_stream(A, list, cnt, cnt_next, fixup_all, c->num_sms, s)
+		                                          : launch_resolve_strip(A, list, cnt, cnt_next, fixup_all, s);
 		if (e != cudaSuccess) return e;
 		*launched = 1;
 		if (need_fixup) {

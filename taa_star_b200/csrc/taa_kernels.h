@@ -20,6 +20,13 @@ cudaError_t launch_resolve_tuned(const ResolveArgs& args, unsigned int* fix_list
 cudaError_t launch_resolve_strip(const ResolveArgs& args, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next,
                                  bool fixup_all, cudaStream_t stream);
 
+// the same contract as a streaming kernel (taa_resolve_stream.cu): the default. One warp per 62-column strip walks down the rows with rolling
+// neighbourhood sums and a sliding history window; raw rows arrive through a per-warp ring of 2-D TMA boxes. stream_supports(): the
+// images can be described by tensor maps (16-byte aligned base and pitch) and the driver exports cuTensorMapEncodeTiled.
+bool stream_supports(const ResolveArgs& args);
+cudaError_t launch_resolve_stream(const ResolveArgs& args, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next,
+                                  bool fixup_all, int num_sms, cudaStream_t stream);
+
 // follow-on passes, one kernel each as the reference dispatches them (taa_post.cu)
 struct PostImg { Img src; Img debug; ImgW dst; int w, h; };
 cudaError_t launch_sharpen(const PostImg& io, float sharpeningFactor, cudaStream_t stream);           // sharpen.comp

@@ -1,0 +1,927 @@
+// taa_resolve_stream.cu — the streaming resolve kernel: the default for the BASELINE configs 2-5 family since round 2
+// (same settings family and the same arithmetic contract as taa_resolve_strip.cu: exact coordinates and predicates, re-associated colour
+// filtering, undecidable pixels handed to the exact fix-up pass).
+//
+// Shape of the work (chosen against the ncu captures of the strip kernel: issue-bound at 353 thread-instructions per pixel, three
+// block-wide barriers and an un-overlapped staging -> phase 1 -> phase 2 sequence per tile):
+//   * A WARP is the unit of work, there is no block-wide barrier anywhere. A warp owns a strip of 62 output columns and walks down R rows.
+//     A lane owns two ADJACENT columns (c0 even): one 16-byte store per output image and row, the partner column's values are already in
+//     registers, and only one neighbour per side comes over a warp shuffle. 64 sampled columns give 62 outputs (the two outermost columns
+//     have no neighbour in the warp).
+//   * The raw colour, velocity (and depth) rows stream through a per-warp RING in shared memory, filled by 2-D tensor-map TMA boxes
+//     (cp.async.bulk.tensor.2d, 72 texels x 2 rows per box) that complete on per-slot mbarriers; the warp itself re-arms a slot as soon as
+//     it has consumed it, so the rows of the next steps are in flight while the current ones are evaluated. TMA zero-fills what lies
+//     outside the image; the sampler's clamp-to-edge is applied through the coordinate tables (they never point at a filled texel).
+//   * Nothing is staged twice: the sampled current colour (taa.comp:207, sampler bleed kept) is evaluated once per texel straight out of
+//     the ring, converted to YCoCg and folded into ROLLING 3-row sums of the variance box (taa.comp:266-277); there is no sampled tile.
+//   * Uniform motion (every velocity texel a strip touches is bit-identical and finite; checked row by row as the rows arrive): the
+//     4 x 4 Catmull-Rom footprints of the two columns share five texels per row, the horizontally filtered rows slide down the strip in
+//     registers (one new row per pixel row, requested one row ahead), the per-row weights come from a table the lanes build in parallel
+//     once per unit. The footprint start is FORCED to advance by exactly one texel per column / row (the natural floor() can jitter by one
+//     where the fractional position is within rounding of 0; the Catmull-Rom weights are continuous there, so the two choices agree to
+//     O(eps^2)) — a static camera stays on this path.
+//   * Anything else (varying motion, footprints that leave the image, movers) takes the general rows: exact bilinear velocity sample out
+//     of the ring, per-pixel 4 x 4 gather through L1. A unit falls back from uniform to general rows one way, at a two-row step.
+// Rows per unit R and the grid are chosen on the host so that the units fill whole waves of resident warps.
+#include "taa_tuned_common.cuh"
+#include "taa_kernels.h"
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
+namespace taa {
+
+namespace {
+
+using namespace tuned;
+
+constexpr int OWS = 62;                     // output columns per warp strip
+constexpr int RWT = 72;                     // ring row: image columns Xb .. Xb + 71, Xb = 62 s - 4 (one TMA box row, 576 bytes)
+constexpr unsigned int ROWB = RWT * 8u;
+constexpr int SROWS = 2;                    // rows per slot = per TMA box
+constexpr int RMAX = 30;                    // output rows per unit: one 32-entry row table covers rows Y0 - 1 .. Y0 + 30
+constexpr int NWARP = 2;                    // warps (independent strips) per CTA
+constexpr int DW = 64;                      // depth ring row: columns Xs .. Xs + 63
+constexpr unsigned int DROWB = DW * 4u;
+
+template <bool REJ>
+struct Cfg {
+	static constexpr int LOOK = REJ ? 1 : 0;        // extra slots of look-ahead: the rejection variants look two velocity rows further down
+	static constexpr int NSLOT = REJ ? 5 : 4;       // ring slots: 2 (3) live + 2 in flight
+	static constexpr int NR = NSLOT * SROWS;        // ring rows
+};
+
+template <bool REJ>
+struct __align__(128) WarpSmem {
+	unsigned char craw[Cfg<REJ>::NR * ROWB];          // colour rows:   ring row (g - (Y0 - 2)) % NR holds image row g
+	unsigned char vraw[Cfg<REJ>::NR * ROWB];          // velocity rows: ring row (g - (Y0 - 3)) % NR holds image row g
+	unsigned char dt[REJ ? Cfg<REJ>::NR * DROWB : 128];  // depth rows, as colour
+	uint4 tabA[32];                                   // uniform motion: Catmull-Rom y weights of output row Y0 - 1 + t, permuted to the window's register order
+	uint4 tabB[32];                                   // output row: velocity footprint rows (ring offsets lo | hi << 16), weight, v, history v
+	uint4 tabC[32];                                   // sampled colour row: ring offsets m | n << 16, bleed weight (half bits); output row: (int)(hv * H), hv outside [0, 1)
+	unsigned long long mbar[8];
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int x, int y, unsigned long long* bar) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+	             "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+	             : "memory");
+}
+
+// wait for a phase of a slot barrier; a wait that never ends (a box that cannot arrive) traps instead of hanging the device
+__device__ __forceinline__ void slot_wait(unsigned long long* bar, unsigned int parity) {
+	unsigned int ok = 0u;
+	for (unsigned int spins = 0u;; ++spins) {
+		asm volatile(
+		    "{\n"
+		    ".reg .pred p;\n"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		    "selp.u32 %0, 1, 0, p;\n"
+		    "}\n"
+		    : "=r"(ok)
+		    : "r"(smem_u32(bar)), "r"(parity)
+		    : "memory");
+		if (ok) return;
+		if (spins > (1u << 24)) asm volatile("trap;");
+	}
+}
+
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// catmull_axis with the footprint start given (kf = index of the texel left of the sample): the weights of tuned::catmull_axis, which
+// are continuous in the position, evaluated for a footprint that may start one texel beside the natural one
+__device__ __forceinline__ AxisW catmull_axis_k(float h, float size, float inv, float kf) {
+	const float it = h * size;
+	const float tc = kf + 0.5f;
+	const float f = it - tc;
+	const float f2 = f * f;
+	const float w0 = f * fmaf(f, fmaf(-0.5f, f, 1.0f), -0.5f);
+	const float w1 = fmaf(f2, fmaf(1.5f, f, -2.5f), 1.0f);
+	const float w2 = f * fmaf(f, fmaf(-1.5f, f, 2.0f), 0.5f);
+	const float w3 = f2 * fmaf(0.5f, f, -0.5f);
+	const float wC = w1 + w2;
+	const float r = w2 * rcp_approx(wC);
+	const float uC = ((tc + r) * inv) * size - 0.5f;
+	const float sC = uC - kf;
+	const float d1 = sC - 1.0f;
+	AxisW o;
+	o.w[0] = fmaf(wC, sat(-sC), w0);
+	o.w[1] = wC * sat(1.0f - fabsf(sC));
+	o.w[2] = wC * sat(1.0f - fabsf(d1));
+	o.w[3] = fmaf(wC, sat(d1), w3);
+	o.k = (int)fminf(fmaxf(kf, -8.0f), size + 8.0f);
+	return o;
+}
+
+// global row gy as a row the buffer holds (clamped into it; reported when the row was really asked for)
+__device__ __forceinline__ int buf_row(const Img& im, int gy, unsigned int* st, bool used) {
+	int ly = gy - im.y0;
+	if ((unsigned int)ly >= (unsigned int)im.rows) {
+		if (st && used) atomicOr(st, 1u);
+		ly = ly < 0 ? 0 : im.rows - 1;
+	}
+	return ly + im.y0;
+}
+__device__ __forceinline__ unsigned int ring_row(int g, int base, int nr) { return (unsigned int)(((g - base) % nr + nr) % nr); }
+
+struct F3 { float x, y, z; };
+struct RowSum { F3 s1, s2; };     // sum and sum of squares of three horizontally adjacent sampled texels
+struct HR { float r, g, b, a; };  // one horizontally filtered history row
+
+__device__ __forceinline__ F3 shfl_up3(F3 v) { F3 o; o.x = __shfl_up_sync(0xffffffffu, v.x, 1); o.y = __shfl_up_sync(0xffffffffu, v.y, 1); o.z = __shfl_up_sync(0xffffffffu, v.z, 1); return o; }
+__device__ __forceinline__ F3 shfl_down3(F3 v) { F3 o; o.x = __shfl_down_sync(0xffffffffu, v.x, 1); o.y = __shfl_down_sync(0xffffffffu, v.y, 1); o.z = __shfl_down_sync(0xffffffffu, v.z, 1); return o; }
+
+// row sums of the two columns of a lane: column A sees (left neighbour, a, b), column B sees (a, b, right neighbour)
+__device__ __forceinline__ void row_sums(const F3 a, const F3 b, RowSum& ra, RowSum& rb) {
+	const F3 L = shfl_up3(b), R = shfl_down3(a);
+	const float abx = a.x + b.x, aby = a.y + b.y, abz = a.z + b.z;
+	const float qx = fmaf(a.x, a.x, b.x * b.x), qy = fmaf(a.y, a.y, b.y * b.y), qz = fmaf(a.z, a.z, b.z * b.z);
+	ra.s1.x = abx + L.x; ra.s1.y = aby + L.y; ra.s1.z = abz + L.z;
+	rb.s1.x = abx + R.x; rb.s1.y = aby + R.y; rb.s1.z = abz + R.z;
+	ra.s2.x = fmaf(L.x, L.x, qx); ra.s2.y = fmaf(L.y, L.y, qy); ra.s2.z = fmaf(L.z, L.z, qz);
+	rb.s2.x = fmaf(R.x, R.x, qx); rb.s2.y = fmaf(R.y, R.y, qy); rb.s2.z = fmaf(R.z, R.z, qz);
+}
+
+// five adjacent history texels of one row filtered for the two columns of a lane: column A uses texels 0..3, column B texels 1..4
+template <bool REJ>
+__device__ __forceinline__ void hfilter_pair(const uint2 q0, const uint2 q1, const uint2 q2, const uint2 q3, const uint2 q4, const float (&wa)[4], const float (&wb)[4],
+                                             HR& a, HR& b) {
+	const float2 e0 = __half22float2(h2(q0.x)), e1 = __half22float2(h2(q1.x)), e2 = __half22float2(h2(q2.x)), e3 = __half22float2(h2(q3.x)), e4 = __half22float2(h2(q4.x));
+	a.r = fmaf(wa[3], e3.x, fmaf(wa[2], e2.x, fmaf(wa[1], e1.x, wa[0] * e0.x)));
+	a.g = fmaf(wa[3], e3.y, fmaf(wa[2], e2.y, fmaf(wa[1], e1.y, wa[0] * e0.y)));
+	b.r = fmaf(wb[3], e4.x, fmaf(wb[2], e3.x, fmaf(wb[1], e2.x, wb[0] * e1.x)));
+	b.g = fmaf(wb[3], e4.y, fmaf(wb[2], e3.y, fmaf(wb[1], e2.y, wb[0] * e1.y)));
+	if (REJ) {
+		const float2 g0 = __half22float2(h2(q0.y)), g1 = __half22float2(h2(q1.y)), g2 = __half22float2(h2(q2.y)), g3 = __half22float2(h2(q3.y)), g4 = __half22float2(h2(q4.y));
+		a.b = fmaf(wa[3], g3.x, fmaf(wa[2], g2.x, fmaf(wa[1], g1.x, wa[0] * g0.x)));
+		a.a = fmaf(wa[3], g3.y, fmaf(wa[2], g2.y, fmaf(wa[1], g1.y, wa[0] * g0.y)));
+		b.b = fmaf(wb[3], g4.x, fmaf(wb[2], g3.x, fmaf(wb[1], g2.x, wb[0] * g1.x)));
+		b.a = fmaf(wb[3], g4.y, fmaf(wb[2], g3.y, fmaf(wb[1], g2.y, wb[0] * g1.y)));
+	} else {
+		const float g0 = __low2float(h2(q0.y)), g1 = __low2float(h2(q1.y)), g2 = __low2float(h2(q2.y)), g3 = __low2float(h2(q3.y)), g4 = __low2float(h2(q4.y));
+		a.b = fmaf(wa[3], g3, fmaf(wa[2], g2, fmaf(wa[1], g1, wa[0] * g0)));
+		b.b = fmaf(wb[3], g4, fmaf(wb[2], g3, fmaf(wb[1], g2, wb[0] * g1)));
+		a.a = 0.f; b.a = 0.f;
+	}
+}
+
+// warp-uniform constants of a dispatch
+struct KConst {
+	float gg9, rg9, tiny;  // gamma^2 / 9 (at least 1e-12), its inverse square root, 1e-14 / gg9
+	float alpha0;          // mAlpha, or 1 with mResetHistory
+	bool reset;
+};
+
+struct PixOut {
+	unsigned int rg, bh, br;  // packed halves: (r, g), (b, history alpha), (b, 1)
+	unsigned int mask;
+	bool check_ring, uncertain;
+};
+
+// Everything of taa.comp::main after the history sample (taa.comp:769-909) for one pixel. cur = sampled current colour (YCoCg), S1 / S2 =
+// sum and sum of squares over the 3 x 3 neighbourhood, hs* = filtered history (rgb, alpha), rejected = outside / depth decisions of the
+// caller (exact predicates), movement / movC = the 5-tap velocity test and its centre tap, du / dv = uv - history uv.
+template <bool REJ, bool ALPHA, bool DIAG>
+__device__ __forceinline__ PixOut resolve_pixel(const ResolveArgs& A, const KConst& kc, const float fix_band, const F3 cur, const F3 S1, const F3 S2, const float hsr,
+                                                const float hsg, const float hsb, const float hsa, bool rejected, const bool movement, const bool movC, const float du,
+                                                const float dv) {
+	const TaaParameters& P = A.ubo.param[0];
+	PixOut o;
+	o.check_ring = false;
+	o.uncertain = DIAG && fix_band > 3.0e38f;  // TAA_FLAG_FIXUP_ALL
+	// ---- variance box (taa.comp:266-277): mean = S1 / 9, extent = gamma sqrt(max(0, S2 / 9 - mean^2)) = sqrt(gg9 e2) with e2 = S2 - S1 mean.
+	// The clip needs 1 / (extent + 1e-7), taken as rsqrt(max(extent^2, 1e-14)) = rg9 rsqrt(max(e2, tiny)): the clipped colour moves by at most
+	// 1e-7 against the reference formulation. (rg9 multiplies the largest ratio once, below.)
+	const float ninth = 1.0f / 9.0f;
+	const float mx = S1.x * ninth, my = S1.y * ninth, mz = S1.z * ninth;
+	const float e2x = fmaf(-mx, S1.x, S2.x), e2y = fmaf(-my, S1.y, S2.y), e2z = fmaf(-mz, S1.z, S2.z);
+	const float ix = rsqrt_approx(fmaxf(e2x, kc.tiny)), iy = rsqrt_approx(fmaxf(e2y, kc.tiny)), iz = rsqrt_approx(fmaxf(e2z, kc.tiny));
+	// ---- maybe_rgb_to_ycocg(historyRaw.rgb), taa.comp:769
+	const float t = hsr + hsb, hg2 = 0.5f * hsg;
+	const float hx = fmaf(0.25f, t, hg2), hy = 0.5f * (hsr - hsb), hz = fmaf(-0.25f, t, hg2);
+	// ---- rejection by history alpha (taa.comp:796-811)
+	float wdm = 0.f;
+	if (REJ && P.mDynamicAntiGhosting) {
+		if (!movement) {
+			if (hsa > 0.0f) rejected = true;
+			// the sign of a filtered 0/1 mask that cancels to ~0 is not safe under re-association: undecided if the 6x6 ring carries alpha at all
+			o.check_ring = fabsf(hsa) < 2.5f * fix_band;
+		}
+		wdm = movC ? 1.0f : 0.0f;
+	}
+	// ---- clipAabb towards the box centre (taa.comp:323-345)
+	const float vx = hx - mx, vy = hy - my, vz = hz - mz;
+	const float ma = fmaxf(fabsf(vx) * ix, fmaxf(fabsf(vy) * iy, fabsf(vz) * iz)) * kc.rg9;
+	const float s = rcp_approx(fmaxf(ma, 1.0f));
+	const float cx = fmaf(vx, s, mx), cy = fmaf(vy, s, my), cz = fmaf(vz, s, mz);
+	bool rectified = false;
+	if (DIAG) {
+		// |clipped - history| = |v| (1 - s) per component; any(greaterThan(abs(diff), 0.001)) == (largest component > 0.001)
+		const float dmax = fmaxf(fabsf(vx), fmaxf(fabsf(vy), fabsf(vz))) * (1.0f - s);
+		rectified = ma > 1.0f && dmax > 0.001f;
+		if (A.mask.p != nullptr && ma > 1.0f && fabsf(dmax - 0.001f) < fix_band) o.uncertain = true;
+	}
+	// ---- blend (taa.comp:848-900)
+	float alpha = kc.alpha0;
+	if (REJ && rejected) alpha = kc.reset ? 1.0f : P.mRejectionAlpha;
+	else if (ALPHA && !kc.reset) {
+		if (P.mVelBasedAlpha) {
+			const float speed = sqrt_approx(fmaf(du, du, dv * dv));
+			alpha = fmaxf(alpha, mixf(alpha, P.mVelBasedAlphaMax, sat(speed * P.mVelBasedAlphaFactor)));
+		}
+		if (P.mLumaWeightingLottes) {
+			const float lc = cur.x, lh = cx;
+			const float w = 1.0f - fabsf(lc - lh) * rcp_approx(fmaxf(fmaxf(lc, lh), 0.2f));
+			alpha = mixf(P.mMaxAlpha, P.mMinAlpha, w * w);
+		}
+		if (P.mReduceBlendNearClamp) {
+			const float ex = (kc.gg9 * fmaxf(e2x, 0.f)) * (ix * kc.rg9);  // the extent of the luma axis: sqrt(gg9 e2)
+			const float lmin = mx - ex, lmax = mx + ex, lh = hx;
+			float dist = 2.0f * fabsf(fminf(lh - lmin, lmax - lh)) * rcp_approx(lmax - lmin);
+			if (lmax - lmin < 0.001f) dist = 1.0f;
+			alpha *= sat(4.0f * dist);
+		}
+	}
+	const float om = 1.0f - alpha;
+	const float oy = fmaf(cx, om, cur.x * alpha), oco = fmaf(cy, om, cur.y * alpha), ocg = fmaf(cz, om, cur.z * alpha);
+	const float tmp = oy - ocg;
+	const float outr = tmp + oco, outg = oy + ocg, outb = tmp - oco;
+	const __half2 rg = __floats2half2_rn(outr, outg), bm = __floats2half2_rn(outb, wdm);
+	o.rg = *reinterpret_cast<const unsigned int*>(&rg);
+	o.bh = *reinterpret_cast<const unsigned int*>(&bm);
+	o.br = (o.bh & 0xffffu) | 0x3c000000u;
+	o.mask = (rejected ? 1u : 0u) | (rectified ? 2u : 0u) | (2u << 2);
+	return o;
+}
+
+// The general history sample (taa.comp:441-514 through the sampler, re-associated): the 4 x 4 footprint gathered through L1.
+// ring = OR of the alpha words of the 6 x 6 texels around the footprint (all ones where they are not all in reach).
+template <bool REJ>
+__device__ __forceinline__ void gather_history(const ResolveArgs& A, const float hu, const float hv, const int W, const int H, const float fW, const float fH,
+                                               const float invw, const float invh, const int hlo, const int hhi, float& hsr, float& hsg, float& hsb, float& hsa,
+                                               unsigned int& ring) {
+	unsigned int* st = A.status;
+	const AxisW ax = catmull_axis(hu, fW, invw), ay = catmull_axis(hv, fH, invh);
+	const int kx = ax.k, K = ay.k - 1;
+	const int rg = REJ ? 1 : 0;
+	const bool interior = kx - 1 - rg >= 0 && kx + 2 + rg <= W - 1 && K - rg >= hlo && K + 3 + rg <= hhi;
+	uint2 q[16];
+	ring = 0u;
+	if (interior) {
+		const unsigned int hpitch = (unsigned int)A.history_in.pitch;
+		const unsigned char* p = A.history_in.p + ((unsigned int)(K - A.history_in.y0) * hpitch + (unsigned int)(kx - 1) * 8u);
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const uint2* hp = reinterpret_cast<const uint2*>(p + i * hpitch);
+			q[4 * i] = __ldg(hp); q[4 * i + 1] = __ldg(hp + 1); q[4 * i + 2] = __ldg(hp + 2); q[4 * i + 3] = __ldg(hp + 3);
+		}
+		if (REJ) {
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				ring |= __ldg(reinterpret_cast<const unsigned int*>(p + i * hpitch - 4)) | __ldg(reinterpret_cast<const unsigned int*>(p + i * hpitch + 36));
+				ring |= (q[4 * i].y | q[4 * i + 1].y) | (q[4 * i + 2].y | q[4 * i + 3].y);
+			}
+#pragma unroll
+			for (int j = 0; j < 6; ++j)
+				ring |= __ldg(reinterpret_cast<const unsigned int*>(p - hpitch - 4 + 8 * j)) | __ldg(reinterpret_cast<const unsigned int*>(p + 4 * hpitch - 4 + 8 * j));
+		}
+	} else {
+		load_history<false>(A.history_in, kx, ay.k, W, H, st, q);
+		ring = 0x7fff0000u;
+	}
+	const HRow r0 = hfilter<REJ>(q[0], q[1], q[2], q[3], ax.w), r1 = hfilter<REJ>(q[4], q[5], q[6], q[7], ax.w);
+	const HRow r2 = hfilter<REJ>(q[8], q[9], q[10], q[11], ax.w), r3 = hfilter<REJ>(q[12], q[13], q[14], q[15], ax.w);
+	hsr = fmaf(ay.w[3], r3.r, fmaf(ay.w[2], r2.r, fmaf(ay.w[1], r1.r, ay.w[0] * r0.r)));
+	hsg = fmaf(ay.w[3], r3.g, fmaf(ay.w[2], r2.g, fmaf(ay.w[1], r1.g, ay.w[0] * r0.g)));
+	hsb = fmaf(ay.w[3], r3.b, fmaf(ay.w[2], r2.b, fmaf(ay.w[1], r1.b, ay.w[0] * r0.b)));
+	hsa = REJ ? fmaf(ay.w[3], r3.a, fmaf(ay.w[2], r2.a, fmaf(ay.w[1], r1.a, ay.w[0] * r0.a))) : 0.f;
+}
+
+template <bool REJ, bool ALPHA, bool DIAG>
+__global__ void __launch_bounds__(32 * NWARP, REJ ? 6 : 8)
+taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmV,
+                          const __grid_constant__ CUtensorMap tmD, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
+                          unsigned int* __restrict__ fix_count_next, const float fix_band, const int R) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	using C = Cfg<REJ>;
+	constexpr int NSLOT = C::NSLOT, NR = C::NR, LOOK = C::LOOK;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	WarpSmem<REJ>& sm = reinterpret_cast<WarpSmem<REJ>*>(smem_raw)[warp];
+	const TaaParameters& P = A.ubo.param[0];
+	unsigned int* st = A.status;
+	const int W = A.out_w, H = A.out_h;
+	const float fW = (float)W, fH = (float)H;
+	const float invw = 1.0f / fW, invh = 1.0f / fH;
+	const int strip = blockIdx.x * NWARP + warp;
+	const int Y0 = A.band_y0 + blockIdx.y * R;
+	const int nr = min(R, A.band_y0 + A.band_rows - Y0);
+	const int Xs = strip * OWS - 2, Xb = Xs - 2;  // first sampled column, first ring column
+
+	asm volatile("griddepcontrol.wait;" ::: "memory");  // launched with programmatic stream serialisation: nothing is touched before the predecessor is done
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && fix_count_next) *fix_count_next = 0u;  // the counter the next frame appends to
+	if (Xs + 1 > W - 1 || nr <= 0) return;  // (warp-uniform; there is no block-wide barrier in this kernel)
+
+	const bool use_depth = REJ && P.mDepthCulling;
+	const int nslots = (nr + 4 + LOOK + 1) / 2;  // ring rows Y0 - 2 .. Y0 + nr + 1 (+ LOOK) in boxes of two
+	const unsigned int slot_bytes = 2u * SROWS * ROWB + (use_depth ? SROWS * DROWB : 0u);
+	auto issue = [&](int k) {  // lane 0: arm slot k and request its boxes
+		const int pos = k % NSLOT;
+		unsigned long long* bar = &sm.mbar[pos];
+		mbar_expect_tx(bar, slot_bytes);
+		tma_load_2d(sm.craw + pos * (SROWS * ROWB), &tmC, 2 * Xb, Y0 - 2 + SROWS * k - A.color.y0, bar);
+		tma_load_2d(sm.vraw + pos * (SROWS * ROWB), &tmV, 2 * Xb, Y0 - 3 + SROWS * k - A.velocity.y0, bar);
+		if (use_depth) tma_load_2d(sm.dt + pos * (SROWS * DROWB), &tmD, Xs, Y0 - 2 + SROWS * k - A.depth.y0, bar);
+	};
+	auto wait_slot = [&](int k) { slot_wait(&sm.mbar[k % NSLOT], (unsigned int)((k / NSLOT) & 1)); };
+
+	if (lane == 0) {
+#pragma unroll
+		for (int p = 0; p < NSLOT; ++p) mbar_init(&sm.mbar[p], 1u);
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		for (int k = 0; k < min(NSLOT, nslots); ++k) issue(k);
+	}
+	__syncwarp();
+
+	// ---- constants of the lane's two columns c0 = Xs + 2 lane, c1 = c0 + 1 (while the first boxes arrive) ----
+	const int c0 = Xs + 2 * lane, c1 = c0 + 1;
+	const bool cv0 = c0 >= 0 && c0 < W, cv1 = c1 >= 0 && c1 < W;  // the column exists in the image
+	unsigned int cm0, cn0, cm1, cn1;  // colour taps: byte offsets of the main texel and of its bleeding neighbour in a ring row
+	__half px0, px1;
+	{
+		int m, n;
+		float p;
+		colour_axis(c0, invw, W, m, n, p);
+		cm0 = (unsigned int)iclamp(m - Xb, 0, RWT - 1) * 8u; cn0 = (unsigned int)iclamp(n - Xb, 0, RWT - 1) * 8u; px0 = __float2half_rn(p);
+		colour_axis(c1, invw, W, m, n, p);
+		cm1 = (unsigned int)iclamp(m - Xb, 0, RWT - 1) * 8u; cn1 = (unsigned int)iclamp(n - Xb, 0, RWT - 1) * 8u; px1 = __float2half_rn(p);
+	}
+	const int x0c = iclamp(c0, 0, W - 1), x1c = iclamp(c1, 0, W - 1);
+	const float u0 = ((float)x0c + 0.5f) / fW, u1 = ((float)x1c + 0.5f) / fW;  // tc_to_uv, taa.comp:131
+	const bool so0 = lane >= 1 && cv0, so1 = lane <= 30 && cv1;                  // the column is an output of this strip
+	const bool al16 = (((unsigned long long)A.history_out.p | (unsigned long long)A.history_out.pitch | (unsigned long long)A.result.p | (unsigned long long)A.result.pitch) & 15ull) == 0ull;
+	const bool st16 = so0 && so1 && al16;
+
+	KConst kc;
+	{
+		kc.gg9 = fmaxf(P.mVarClipGamma * P.mVarClipGamma * (1.0f / 9.0f), 1e-12f);
+		kc.rg9 = rsqrt_approx(kc.gg9);
+		kc.tiny = 1e-14f * rcp_approx(kc.gg9);
+		kc.reset = A.ubo.mResetHistory != 0;
+		kc.alpha0 = kc.reset ? 1.0f : P.mAlpha;
+	}
+	const int hlo = max(0, A.history_in.y0), hhi = min(H - 1, A.history_in.y0 + A.history_in.rows - 1);
+	const unsigned int hpitch = (unsigned int)A.history_in.pitch;
+	const unsigned char* hbase = A.history_in.p;
+
+	// ---- row tables, the part that does not depend on the motion: entry t = image row Y0 - 1 + t ----
+	{
+		const int g = Y0 - 1 + lane;
+		int m, n;
+		float p;
+		colour_axis(g, invh, H, m, n, p);
+		const bool cused = lane <= nr + 1;  // sampled rows Y0 - 1 .. Y0 + nr
+		const unsigned int cm = ring_row(buf_row(A.color, m, st, cused), Y0 - 2, NR) * ROWB, cn = ring_row(buf_row(A.color, n, st, cused), Y0 - 2, NR) * ROWB;
+		const __half ph = __float2half_rn(p);
+		sm.tabC[lane] = make_uint4(cm | (cn << 16), (unsigned int)__half_as_ushort(ph), 0u, 0u);
+		const float v = ((float)g + 0.5f) / fH;
+		const Lin L = lin_coord(v, H);
+		const bool vused = lane >= 1 && lane <= nr;  // output rows
+		const unsigned int o0 = ring_row(buf_row(A.velocity, L.i0, st, vused), Y0 - 3, NR) * ROWB, o1 = ring_row(buf_row(A.velocity, L.i1, st, vused), Y0 - 3, NR) * ROWB;
+		sm.tabB[lane] = make_uint4(o0 | (o1 << 16), __float_as_uint(L.a), __float_as_uint(v), 0u);
+		if (use_depth && vused) buf_row(A.depth, g, st, true);
+	}
+	__syncwarp();
+
+	// ---- the first rows: slots 0, 1 (and 2) ----
+	wait_slot(0);
+	if (nslots > 1) wait_slot(1);
+	if (LOOK && nslots > 2) wait_slot(2);
+
+	// ---- is the motion uniform? ----
+	// Reference texel: velocity row Y0 at a column that exists. A row passes if the lane's two texels (and, for the rejection variants, the
+	// two texels beside the strip's outputs) are bit-identical to it. Rows outside the image are never sampled as themselves; rows the buffer
+	// does not hold end the uniform path (the general rows report them).
+	const uint2 vref = *reinterpret_cast<const uint2*>(sm.vraw + ring_row(Y0, Y0 - 3, NR) * ROWB + (unsigned int)(iclamp(Xs + 2, 0, W - 1) - Xb) * 8u);
+	bool uni = finite2(vref.x) && (!REJ || finite2(vref.y));
+	if (REJ && P.mDynamicAntiGhosting) uni = uni && (vref.y & 0x7fff0000u) == 0u;  // the strip's own motion is not a mover's
+	unsigned int wrows = 0u;  // bit r: velocity row (newest voted - r) carries velocity.w != 0 somewhere under / beside the strip
+	auto vote_row = [&](int g) {
+		if (g < 0 || g > H - 1) return;
+		if (g < A.velocity.y0 || g >= A.velocity.y0 + A.velocity.rows) { uni = false; wrows = (wrows << 1) | 1u; return; }
+		const unsigned char* row = sm.vraw + ring_row(g, Y0 - 3, NR) * ROWB;
+		const uint4 t = *reinterpret_cast<const uint4*>(row + (unsigned int)(2 + 2 * lane) * 8u);
+		bool ok = (!cv0 || (t.x == vref.x && (!REJ || t.y == vref.y))) && (!cv1 || (t.z == vref.x && (!REJ || t.w == vref.y)));
+		if (REJ) {
+			unsigned int wb = ((cv0 ? t.y : 0u) | (cv1 ? t.w : 0u)) & 0x7fff0000u;
+			if (lane == 0 || lane == 31) {  // columns Xs - 1 and Xs + 64: inside the 5 x 5 texels around the outermost outputs
+				const int ce = lane == 0 ? Xs - 1 : Xs + 64;
+				if (ce >= 0 && ce < W) {
+					const uint2 e = *reinterpret_cast<const uint2*>(row + (unsigned int)(ce - Xb) * 8u);
+					ok = ok && e.x == vref.x && e.y == vref.y;
+					wb |= e.y & 0x7fff0000u;
+				}
+			}
+			wrows = (wrows << 1) | (__any_sync(0xffffffffu, wb != 0u) ? 1u : 0u);
+		}
+		uni = uni && __all_sync(0xffffffffu, ok);
+	};
+	if (REJ) { vote_row(Y0 - 2); vote_row(Y0 - 1); vote_row(Y0); vote_row(Y0 + 1); vote_row(Y0 + 2); }
+	else { vote_row(Y0 - 1); vote_row(Y0); }
+
+	// ---- uniform motion: column constants and the motion-dependent part of the row tables ----
+	float wA[4] = {0.f, 0.f, 0.f, 0.f}, wB[4] = {0.f, 0.f, 0.f, 0.f};
+	float hu0 = 0.f, hu1 = 0.f, f_velz = 0.f;
+	int tx0 = 0, tx1 = 0;
+	bool outx0 = false, outx1 = false;
+	unsigned int hoff = 0u;  // byte offset of the history row in flight (first texel of the lane's five)
+	if (uni) {
+		const float2 vxy = __half22float2(h2(vref.x));
+		if (REJ) f_velz = __low2float(h2(vref.y));
+		hu0 = u0 - vxy.x; hu1 = u1 - vxy.x;
+		const AxisW a = catmull_axis(hu0, fW, invw);
+		const AxisW b = catmull_axis_k(hu1, fW, invw, (float)(a.k + 1));
+#pragma unroll
+		for (int i = 0; i < 4; ++i) { wA[i] = a.w[i]; wB[i] = b.w[i]; }
+		tx0 = (int)(hu0 * fW); tx1 = (int)(hu1 * fW);
+		outx0 = hu0 < 0.f || hu0 >= 1.f; outx1 = hu1 < 0.f || hu1 >= 1.f;
+		const int rg = REJ ? 1 : 0;
+		bool ok = a.k - 1 - rg >= 0 && a.k + 3 + rg <= W - 1;
+		// rows: the footprint of output row Y0 + i starts at K0 + i
+		const float v_first = ((float)Y0 + 0.5f) / fH;
+		const int K0 = catmull_axis(v_first - vxy.y, fH, invh).k - 1;
+		ok = ok && K0 - rg >= hlo && K0 + nr + 2 + rg <= hhi;
+		const int g = Y0 - 1 + lane, i = lane - 1;
+		const float v = ((float)g + 0.5f) / fH;
+		const float hv = v - vxy.y;
+		const AxisW wy = catmull_axis_k(hv, fH, invh, (float)(K0 + 1 + i));
+		// the window keeps history row K0 + i + j in register slot (i + j) & 3: slot p carries weight (p - i) & 3
+		sm.tabA[lane] = make_uint4(__float_as_uint(wy.w[(0 - i) & 3]), __float_as_uint(wy.w[(1 - i) & 3]), __float_as_uint(wy.w[(2 - i) & 3]), __float_as_uint(wy.w[(3 - i) & 3]));
+		uint4 tb = sm.tabB[lane];
+		tb.w = __float_as_uint(hv);
+		sm.tabB[lane] = tb;
+		uint4 tc = sm.tabC[lane];
+		tc.z = (unsigned int)(int)(hv * fH);
+		tc.w = (hv < 0.f || hv >= 1.f) ? 1u : 0u;
+		sm.tabC[lane] = tc;
+		uni = __all_sync(0xffffffffu, ok);
+		hoff = (unsigned int)(K0 - A.history_in.y0) * hpitch + (unsigned int)(a.k - 1) * 8u;
+	}
+	__syncwarp();
+
+	// ---- sampled colour rows Y0 - 1 and Y0 (taa.comp:207 through the sampler, YCoCg), their row sums ----
+	const unsigned char* cr = sm.craw;
+	auto sample_pair = [&](const uint4 tc, F3& a, F3& b) {
+		const unsigned int cm = tc.x & 0xffffu, cn = tc.x >> 16;
+		const __half py = __ushort_as_half((unsigned short)tc.y);
+		const float3 va = sample_ycocg(*reinterpret_cast<const uint2*>(cr + (cm + cm0)), *reinterpret_cast<const uint2*>(cr + (cm + cn0)),
+		                               *reinterpret_cast<const uint2*>(cr + (cn + cm0)), px0, py);
+		const float3 vb = sample_ycocg(*reinterpret_cast<const uint2*>(cr + (cm + cm1)), *reinterpret_cast<const uint2*>(cr + (cm + cn1)),
+		                               *reinterpret_cast<const uint2*>(cr + (cn + cm1)), px1, py);
+		a.x = va.x; a.y = va.y; a.z = va.z;
+		b.x = vb.x; b.y = vb.y; b.z = vb.z;
+	};
+	// Rolling state of the variance box, per column: Q[e] = row sums of sampled row y (e = parity of the unit row), PQ = sums of rows y - 1 and
+	// y added up, CUR[e] = sampled colour of row y. A row adds sampled row y + 1 into slot e ^ 1: no register is ever moved.
+	RowSum QA[2], QB[2], PQA, PQB;
+	F3 CURA[2], CURB[2];
+	{
+		F3 a, b;
+		RowSum rA, rB;
+		sample_pair(sm.tabC[0], a, b);
+		row_sums(a, b, rA, rB);
+		sample_pair(sm.tabC[1], CURA[0], CURB[0]);
+		row_sums(CURA[0], CURB[0], QA[0], QB[0]);
+		PQA.s1.x = rA.s1.x + QA[0].s1.x; PQA.s1.y = rA.s1.y + QA[0].s1.y; PQA.s1.z = rA.s1.z + QA[0].s1.z;
+		PQA.s2.x = rA.s2.x + QA[0].s2.x; PQA.s2.y = rA.s2.y + QA[0].s2.y; PQA.s2.z = rA.s2.z + QA[0].s2.z;
+		PQB.s1.x = rB.s1.x + QB[0].s1.x; PQB.s1.y = rB.s1.y + QB[0].s1.y; PQB.s1.z = rB.s1.z + QB[0].s1.z;
+		PQB.s2.x = rB.s2.x + QB[0].s2.x; PQB.s2.y = rB.s2.y + QB[0].s2.y; PQB.s2.z = rB.s2.z + QB[0].s2.z;
+		QA[1] = QA[0]; QB[1] = QB[0]; CURA[1] = CURA[0]; CURB[1] = CURB[0];
+	}
+	// one row of the rolling box: samples row y + 1 (table entry tc), returns the 3 x 3 sums of row y
+	auto advance_box = [&](auto EC, const uint4 tc, F3& S1a, F3& S2a, F3& S1b, F3& S2b) {
+		constexpr int E = decltype(EC)::value;
+		sample_pair(tc, CURA[E ^ 1], CURB[E ^ 1]);
+		row_sums(CURA[E ^ 1], CURB[E ^ 1], QA[E ^ 1], QB[E ^ 1]);
+		const RowSum &ra = QA[E ^ 1], &rb = QB[E ^ 1], &qa = QA[E], &qb = QB[E];
+		S1a.x = PQA.s1.x + ra.s1.x; S1a.y = PQA.s1.y + ra.s1.y; S1a.z = PQA.s1.z + ra.s1.z;
+		S2a.x = PQA.s2.x + ra.s2.x; S2a.y = PQA.s2.y + ra.s2.y; S2a.z = PQA.s2.z + ra.s2.z;
+		S1b.x = PQB.s1.x + rb.s1.x; S1b.y = PQB.s1.y + rb.s1.y; S1b.z = PQB.s1.z + rb.s1.z;
+		S2b.x = PQB.s2.x + rb.s2.x; S2b.y = PQB.s2.y + rb.s2.y; S2b.z = PQB.s2.z + rb.s2.z;
+		PQA.s1.x = qa.s1.x + ra.s1.x; PQA.s1.y = qa.s1.y + ra.s1.y; PQA.s1.z = qa.s1.z + ra.s1.z;
+		PQA.s2.x = qa.s2.x + ra.s2.x; PQA.s2.y = qa.s2.y + ra.s2.y; PQA.s2.z = qa.s2.z + ra.s2.z;
+		PQB.s1.x = qb.s1.x + rb.s1.x; PQB.s1.y = qb.s1.y + rb.s1.y; PQB.s1.z = qb.s1.z + rb.s1.z;
+		PQB.s2.x = qb.s2.x + rb.s2.x; PQB.s2.y = qb.s2.y + rb.s2.y; PQB.s2.z = qb.s2.z + rb.s2.z;
+	};
+	__syncwarp();
+	if (lane == 0 && NSLOT < nslots) issue(NSLOT);  // slot 0 (rows Y0 - 2, Y0 - 1) is consumed
+
+	// ---- output pointers (32-bit offsets: tuned_supports() admits only buffers below 4 GB) ----
+	unsigned int o_hist = (unsigned int)(Y0 - A.history_out.y0) * (unsigned int)A.history_out.pitch + (unsigned int)x0c * 8u;
+	unsigned int o_res = (unsigned int)(Y0 - A.result.y0) * (unsigned int)A.result.pitch + (unsigned int)x0c * 8u;
+	unsigned int o_mask = (unsigned int)(Y0 - A.mask.y0) * (unsigned int)A.mask.pitch + (unsigned int)x0c * 4u;
+	unsigned int fixA = 0u, fixB = 0u;  // rows of the unit whose pixel goes to the exact pass
+	// stores as predicated instructions (no divergent branches around them): lanes 1 .. 30 write both pixels with one 16-byte store
+	const unsigned int p16h = st16 ? 1u : 0u, p0h = (so0 && !st16) ? 1u : 0u, p1h = (so1 && !st16) ? 1u : 0u;
+	const unsigned int hasres = A.result.p ? 1u : 0u, p16r = p16h & hasres, p0r = p0h & hasres, p1r = p1h & hasres;
+	auto store_px = [&](unsigned char* base, const unsigned int off, const unsigned int q16, const unsigned int q0, const unsigned int q1, const unsigned int arg,
+	                    const unsigned int ab, const unsigned int brg, const unsigned int bb) {
+		unsigned char* ptr = base + off;
+		asm volatile(
+		    "{\n"
+		    ".reg .pred a, b, c;\n"
+		    "setp.ne.u32 a, %1, 0;\n"
+		    "setp.ne.u32 b, %2, 0;\n"
+		    "setp.ne.u32 c, %3, 0;\n"
+		    "@a st.global.v4.u32 [%0], {%4, %5, %6, %7};\n"
+		    "@b st.global.v2.u32 [%0], {%4, %5};\n"
+		    "@c st.global.v2.u32 [%0 + 8], {%6, %7};\n"
+		    "}\n" ::"l"(ptr), "r"(q16), "r"(q0), "r"(q1), "r"(arg), "r"(ab), "r"(brg), "r"(bb)
+		    : "memory");
+	};
+	auto store_row = [&](const PixOut& a, const PixOut& b, const int i) {
+		store_px(A.history_out.p, o_hist, p16h, p0h, p1h, a.rg, a.bh, b.rg, b.bh);
+		store_px(A.result.p, o_res, p16r, p0r, p1r, a.rg, a.br, b.rg, b.br);
+		if (DIAG) {
+			if (A.mask.p) {
+				if (so0) *reinterpret_cast<unsigned int*>(A.mask.p + o_mask) = a.mask;
+				if (so1) *reinterpret_cast<unsigned int*>(A.mask.p + o_mask + 4u) = b.mask;
+			}
+			if (a.uncertain && so0) fixA |= 1u << i;
+			if (b.uncertain && so1) fixB |= 1u << i;
+		}
+		o_hist += (unsigned int)A.history_out.pitch;
+		o_res += (unsigned int)A.result.pitch;
+		o_mask += (unsigned int)A.mask.pitch;
+	};
+	// begin a two-row step: the slot with the rows it adds has landed; the velocity rows it adds are put to the vote
+	auto step_begin = [&](const int i) {
+		const int k = i / 2 + 2 + LOOK;
+		if (k < nslots) {
+			wait_slot(k);
+			vote_row(Y0 + i + 1 + 2 * LOOK);
+			vote_row(Y0 + i + 2 + 2 * LOOK);
+		}
+	};
+	// end it: ring rows (Y0 - 2) + i + 2, + 3 are consumed, their slot is re-armed with the rows NSLOT slots further down
+	auto step_end = [&](const int i) {
+		__syncwarp();
+		const int k = i / 2 + 1 + NSLOT;
+		if (lane == 0 && k < nslots) issue(k);
+	};
+
+	int i = 0;
+	bool begun = false;  // the step at row i has begun (its slot awaited, its rows voted) and then left the uniform path
+	if (uni) {
+		// ================================ uniform motion ================================
+		HR hA[4], hB[4];
+		unsigned int orw[4] = {0u, 0u, 0u, 0u}, or_prev = 0u;  // OR of the alpha words of the window's rows / of the row above it (columns k - 2 .. k + 4)
+		{
+			const unsigned char* p = hbase + hoff;
+			if (REJ) {
+				const unsigned int* a = reinterpret_cast<const unsigned int*>(p - hpitch - 4);
+				or_prev = (__ldg(a) | __ldg(a + 2) | __ldg(a + 4)) | (__ldg(a + 6) | __ldg(a + 8) | __ldg(a + 10)) | __ldg(a + 12);
+			}
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const uint2* hp = reinterpret_cast<const uint2*>(p + j * hpitch);
+				const uint2 q0 = __ldg(hp), q1 = __ldg(hp + 1), q2 = __ldg(hp + 2), q3 = __ldg(hp + 3), q4 = __ldg(hp + 4);
+				if (REJ) {
+					const unsigned int e0 = __ldg(reinterpret_cast<const unsigned int*>(p + j * hpitch - 4)), e1 = __ldg(reinterpret_cast<const unsigned int*>(p + j * hpitch + 44));
+					orw[j] = (q0.y | q1.y | q2.y) | (q3.y | q4.y) | (e0 | e1);
+				}
+				hfilter_pair<REJ>(q0, q1, q2, q3, q4, wA, wB, hA[j], hB[j]);
+			}
+			hoff += 4u * hpitch;
+		}
+		float hdA = 0.f, hdB = 0.f;  // previous depth at the history position of the next pixel row (requested one row ahead)
+		if (use_depth) {
+			const int ty = (int)sm.tabC[1].z;
+			hdA = fetch_r32f(A.history_depth, W, H, tx0, ty, st);
+			hdB = fetch_r32f(A.history_depth, W, H, tx1, ty, st);
+			hdA = __fadd_rn(hdA, 0.0f); hdB = __fadd_rn(hdB, 0.0f);  // consumed here, not by the first row of the loop (see taa_resolve_strip.cu)
+		}
+
+		auto fast_row = [&](auto PHC, const int i) {
+			constexpr int PH = decltype(PHC)::value;  // the register slot the row in flight replaces: i & 3
+			const int t = i + 1;
+			// the history row the next pixel row adds: K0 + i + 4
+			uint2 q0 = make_uint2(0u, 0u), q1 = q0, q2 = q0, q3 = q0, q4 = q0;
+			unsigned int e0 = 0u, e1 = 0u;
+			const bool ahead = REJ || i + 1 < nr;
+			if (ahead) {
+				const unsigned char* p = hbase + hoff;
+				const uint2* hp = reinterpret_cast<const uint2*>(p);
+				q0 = __ldg(hp); q1 = __ldg(hp + 1); q2 = __ldg(hp + 2); q3 = __ldg(hp + 3); q4 = __ldg(hp + 4);
+				if (REJ) {
+					e0 = __ldg(reinterpret_cast<const unsigned int*>(p - 4));
+					e1 = __ldg(reinterpret_cast<const unsigned int*>(p + 44));
+				}
+			}
+			hoff += hpitch;
+			if (i + 2 < nr) asm volatile("prefetch.global.L1 [%0];" ::"l"(hbase + (hoff + ((lane & 1) ? 32u : 0u))));  // the row after it
+			float hdA_n = 0.f, hdB_n = 0.f;
+			if (use_depth && i + 1 < nr) {
+				const int ty = (int)sm.tabC[t + 1].z;
+				hdA_n = fetch_r32f(A.history_depth, W, H, tx0, ty, st);
+				hdB_n = fetch_r32f(A.history_depth, W, H, tx1, ty, st);
+			}
+			const uint4 wyu = sm.tabA[t];
+			const float wy0 = __uint_as_float(wyu.x), wy1 = __uint_as_float(wyu.y), wy2 = __uint_as_float(wyu.z), wy3 = __uint_as_float(wyu.w);
+			// sampled row y + 1 joins the rolling box
+			F3 S1a, S2a, S1b, S2b;
+			advance_box(std::integral_constant<int, PH & 1>{}, sm.tabC[t + 1], S1a, S2a, S1b, S2b);
+			// the footprints, filtered vertically
+			const float ar = fmaf(wy3, hA[3].r, fmaf(wy2, hA[2].r, fmaf(wy1, hA[1].r, wy0 * hA[0].r)));
+			const float ag = fmaf(wy3, hA[3].g, fmaf(wy2, hA[2].g, fmaf(wy1, hA[1].g, wy0 * hA[0].g)));
+			const float ab = fmaf(wy3, hA[3].b, fmaf(wy2, hA[2].b, fmaf(wy1, hA[1].b, wy0 * hA[0].b)));
+			const float br = fmaf(wy3, hB[3].r, fmaf(wy2, hB[2].r, fmaf(wy1, hB[1].r, wy0 * hB[0].r)));
+			const float bg = fmaf(wy3, hB[3].g, fmaf(wy2, hB[2].g, fmaf(wy1, hB[1].g, wy0 * hB[0].g)));
+			const float bb = fmaf(wy3, hB[3].b, fmaf(wy2, hB[2].b, fmaf(wy1, hB[1].b, wy0 * hB[0].b)));
+			float aa = 0.f, ba = 0.f;
+			if (REJ) {
+				aa = fmaf(wy3, hA[3].a, fmaf(wy2, hA[2].a, fmaf(wy1, hA[1].a, wy0 * hA[0].a)));
+				ba = fmaf(wy3, hB[3].a, fmaf(wy2, hB[2].a, fmaf(wy1, hB[1].a, wy0 * hB[0].a)));
+			}
+			// rejection (taa.comp:787-823), exact predicates
+			bool rejA = false, rejB = false;
+			float dv = 0.f;
+			if (REJ || ALPHA) {
+				const uint4 tb = sm.tabB[t];
+				dv = __uint_as_float(tb.z) - __uint_as_float(tb.w);
+			}
+			if (REJ) {
+				const uint4 tc = sm.tabC[t];
+				if (P.mRejectOutside) { rejA = outx0 || tc.w != 0u; rejB = outx1 || tc.w != 0u; }
+				if (use_depth) {
+					const float2 d = *reinterpret_cast<const float2*>(sm.dt + ring_row(Y0 + i, Y0 - 2, NR) * DROWB + (unsigned int)lane * 8u);
+					const float ea = d.x - f_velz, eb = d.y - f_velz;
+					if (fabsf(hdA - ea) > 0.1f * (1.0f - hdA)) rejA = true;
+					if (fabsf(hdB - eb) > 0.1f * (1.0f - hdB)) rejB = true;
+				}
+			}
+			PixOut oa = resolve_pixel<REJ, ALPHA, DIAG>(A, kc, fix_band, CURA[PH & 1], S1a, S2a, ar, ag, ab, aa, rejA, false, false, u0 - hu0, dv);
+			PixOut ob = resolve_pixel<REJ, ALPHA, DIAG>(A, kc, fix_band, CURB[PH & 1], S1b, S2b, br, bg, bb, ba, rejB, false, false, u1 - hu1, dv);
+			// slide the window: the row that was in flight replaces the oldest
+			if (REJ) {
+				const unsigned int or_new = (q0.y | q1.y | q2.y) | (q3.y | q4.y) | (e0 | e1);
+				if ((oa.check_ring || ob.check_ring) && (((or_prev | or_new) | (orw[0] | orw[1]) | (orw[2] | orw[3])) & 0x7fff0000u)) {
+					if (oa.check_ring) oa.uncertain = true;
+					if (ob.check_ring) ob.uncertain = true;
+				}
+				or_prev = orw[PH];
+				orw[PH] = or_new;
+				hdA = hdA_n; hdB = hdB_n;
+			}
+			store_row(oa, ob, i);
+			hfilter_pair<REJ>(q0, q1, q2, q3, q4, wA, wB, hA[PH], hB[PH]);
+		};
+
+		while (i < nr) {
+			step_begin(i);
+			if (!uni) { begun = true; break; }
+			fast_row(std::integral_constant<int, 0>{}, i);
+			if (i + 1 < nr) fast_row(std::integral_constant<int, 1>{}, i + 1);
+			step_end(i);
+			i += 2;
+			if (i >= nr) break;
+			step_begin(i);
+			if (!uni) { begun = true; break; }
+			fast_row(std::integral_constant<int, 2>{}, i);
+			if (i + 1 < nr) fast_row(std::integral_constant<int, 3>{}, i + 1);
+			step_end(i);
+			i += 2;
+		}
+	}
+
+	if (i < nr) {
+		// ================================ general rows ================================
+		const unsigned char* vraw = sm.vraw;
+		unsigned int vo00, vo01, vo10, vo11;  // velocity footprint columns of the lane's two pixels (byte offsets in a ring row)
+		float va0, va1;
+		{
+			const Lin L0 = lin_coord(u0, W), L1 = lin_coord(u1, W);
+			vo00 = (unsigned int)iclamp(L0.i0 - Xb, 0, RWT - 1) * 8u; vo01 = (unsigned int)iclamp(L0.i1 - Xb, 0, RWT - 1) * 8u; va0 = L0.a;
+			vo10 = (unsigned int)iclamp(L1.i0 - Xb, 0, RWT - 1) * 8u; vo11 = (unsigned int)iclamp(L1.i1 - Xb, 0, RWT - 1) * 8u; va1 = L1.a;
+		}
+		auto general_pixel = [&](const int i, const unsigned int o0, const unsigned int o1, const float a, const float u, const F3 cur, const F3 S1, const F3 S2,
+		                         const float depth, const bool movers_near) -> PixOut {
+			const uint4 tb = sm.tabB[i + 1];
+			const unsigned int r0 = tb.x & 0xffffu, r1 = tb.x >> 16;
+			const float ra = __uint_as_float(tb.y), v = __uint_as_float(tb.z);
+			// ---- getHistoryPosition (taa.comp:391-438), exact ----
+			const uint2 vt00 = *reinterpret_cast<const uint2*>(vraw + (r0 + o0)), vt10 = *reinterpret_cast<const uint2*>(vraw + (r0 + o1));
+			const uint2 vt01 = *reinterpret_cast<const uint2*>(vraw + (r1 + o0)), vt11 = *reinterpret_cast<const uint2*>(vraw + (r1 + o1));
+			float velx, vely, velz = 0.f;
+			bool movC = false;
+			bool same = vt00.x == vt10.x && vt00.x == vt01.x && vt00.x == vt11.x && finite2(vt00.x);
+			if (REJ) same = same && vt00.y == vt10.y && vt00.y == vt01.y && vt00.y == vt11.y && finite2(vt00.y);
+			if (same) {  // lerp(p, p, w) == p + w * 0 == p for finite p
+				const float2 xy = __half22float2(h2(vt00.x));
+				velx = xy.x; vely = xy.y;
+				if (REJ) {
+					const float2 zw = __half22float2(h2(vt00.y));
+					velz = zw.x;
+					movC = (fabsf(velx) > 1e-5f || fabsf(vely) > 1e-5f) && (fabsf(zw.y) >= 0.5f);
+				}
+			} else {
+				const float2 a00 = __half22float2(h2(vt00.x)), a10 = __half22float2(h2(vt10.x)), a01 = __half22float2(h2(vt01.x)), a11 = __half22float2(h2(vt11.x));
+				velx = lerpf(lerpf(a00.x, a10.x, a), lerpf(a01.x, a11.x, a), ra);
+				vely = lerpf(lerpf(a00.y, a10.y, a), lerpf(a01.y, a11.y, a), ra);
+				if (REJ) {
+					const float2 b00 = __half22float2(h2(vt00.y)), b10 = __half22float2(h2(vt10.y)), b01 = __half22float2(h2(vt01.y)), b11 = __half22float2(h2(vt11.y));
+					velz = lerpf(lerpf(b00.x, b10.x, a), lerpf(b01.x, b11.x, a), ra);
+					const float velw = lerpf(lerpf(b00.y, b10.y, a), lerpf(b01.y, b11.y, a), ra);
+					movC = (fabsf(velx) > 1e-5f || fabsf(vely) > 1e-5f) && (fabsf(velw) >= 0.5f);
+				}
+			}
+			const float hu = u - velx, hv = v - vely;
+			float hsr, hsg, hsb, hsa;
+			unsigned int ring;
+			gather_history<REJ>(A, hu, hv, W, H, fW, fH, invw, invh, hlo, hhi, hsr, hsg, hsb, hsa, ring);
+			bool rejected = false, movement = false;
+			if (REJ) {
+				if (P.mRejectOutside && (hu < 0.f || hv < 0.f || hu >= 1.f || hv >= 1.f)) rejected = true;
+				if (P.mDynamicAntiGhosting) {
+					movement = movC;
+					// the four other taps of the movement test (taa.comp:796-806): where no texel within two of the strip's recent rows carries
+					// velocity.w, every tap's w is exactly 0
+					if (!movement && movers_near) {
+						auto mov = [&](float s, float t) {
+							const float4 q = tex_rgba16f(A.velocity, W, H, s, t, st);
+							return (fabsf(q.x) > 1e-5f || fabsf(q.y) > 1e-5f) && (fabsf(q.w) >= 0.5f);
+						};
+						movement = mov(u + invw * -1.f, v + invh * 0.f) || mov(u + invw * 1.f, v + invh * 0.f) || mov(u + invw * 0.f, v + invh * -1.f) ||
+						           mov(u + invw * 0.f, v + invh * 1.f);
+					}
+				}
+				if (P.mDepthCulling) {
+					const float expected = depth - velz;
+					const float hd = fetch_r32f(A.history_depth, W, H, (int)(hu * fW), (int)(hv * fH), st);
+					if (fabsf(hd - expected) > 0.1f * (1.0f - hd)) rejected = true;
+				}
+			}
+			PixOut o = resolve_pixel<REJ, ALPHA, DIAG>(A, kc, fix_band, cur, S1, S2, hsr, hsg, hsb, hsa, rejected, movement, movC, u - hu, v - hv);
+			if (REJ && o.check_ring && (ring & 0x7fff0000u)) o.uncertain = true;
+			return o;
+		};
+		auto general_row = [&](auto EC, const int i) {
+			constexpr int E = decltype(EC)::value;  // parity of the unit row
+			const int t = i + 1;
+			F3 S1a, S2a, S1b, S2b;
+			advance_box(EC, sm.tabC[t + 1], S1a, S2a, S1b, S2b);
+			float2 d = make_float2(0.f, 0.f);
+			if (use_depth) d = *reinterpret_cast<const float2*>(sm.dt + ring_row(Y0 + i, Y0 - 2, NR) * DROWB + (unsigned int)lane * 8u);
+			// velocity rows up to Y0 + i + 4 (+ 1) have been voted: bits 0 .. 7 cover rows y - 2 .. y + 2 of both rows of the step
+			const bool movers_near = REJ && (wrows & 0xffu) != 0u;
+			const PixOut oa = general_pixel(i, vo00, vo01, va0, u0, CURA[E], S1a, S2a, d.x, movers_near);
+			const PixOut ob = general_pixel(i, vo10, vo11, va1, u1, CURB[E], S1b, S2b, d.y, movers_near);
+			store_row(oa, ob, i);
+		};
+		while (i < nr) {
+			if (!begun) step_begin(i);
+			begun = false;
+			general_row(std::integral_constant<int, 0>{}, i);
+			if (i + 1 < nr) general_row(std::integral_constant<int, 1>{}, i + 1);
+			step_end(i);
+			i += 2;
+		}
+	}
+
+	// ---- hand the undecidable pixels of the unit to the exact pass (one atomic per warp) ----
+	if (DIAG && fix_list != nullptr && __ballot_sync(0xffffffffu, (fixA | fixB) != 0u)) {
+		const int n = __popc(fixA) + __popc(fixB);
+		int pre = n;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const int t = __shfl_up_sync(0xffffffffu, pre, d);
+			if (lane >= d) pre += t;
+		}
+		unsigned int base = 0u;
+		if (lane == 31) base = atomicAdd(fix_count, (unsigned int)pre);
+		base = __shfl_sync(0xffffffffu, base, 31);
+		unsigned int slot = base + (unsigned int)(pre - n);
+		while (fixA) {
+			const int b = __ffs(fixA) - 1;
+			fixA &= fixA - 1u;
+			fix_list[slot++] = (unsigned int)(Y0 + b) * (unsigned int)W + (unsigned int)c0;
+		}
+		while (fixB) {
+			const int b = __ffs(fixB) - 1;
+			fixB &= fixB - 1u;
+			fix_list[slot++] = (unsigned int)(Y0 + b) * (unsigned int)W + (unsigned int)c1;
+		}
+	}
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+	static EncodeTiledFn fn = [] {
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+		return (EncodeTiledFn)p;
+	}();
+	return fn;
+}
+
+// a row-major image of 4-byte words (an 8-byte texel is two), boxes of box_w words x SROWS rows, out-of-range words read as 0
+bool make_map(CUtensorMap* tm, const Img& im, int words_per_row, int box_w) {
+	EncodeTiledFn fn = encode_fn();
+	if (!fn) return false;
+	const cuuint64_t dims[2] = {(cuuint64_t)words_per_row, (cuuint64_t)im.rows};
+	const cuuint64_t strides[1] = {(cuuint64_t)im.pitch};
+	const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)SROWS};
+	const cuuint32_t estr[2] = {1u, 1u};
+	return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)im.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+	          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool tma_able(const Img& im) { return im.p && (((unsigned long long)im.p | (unsigned long long)im.pitch) & 15ull) == 0ull && im.rows > 0; }
+
+// Rows per unit: the grid is (strip pairs) x ceil(band / R) CTAs on `resident` CTA slots; take the R whose last wave is fullest, weighted
+// by the per-unit overhead (two extra sampled rows, three extra history rows: ~0.8 of a row)
+int pick_rows(int nx, int band_rows, int resident) {
+	static const int forced = [] { const char* s = getenv("TAA_STREAM_R"); return s ? atoi(s) : 0; }();
+	if (forced >= 2 && forced <= RMAX) return forced;
+	int best = RMAX;
+	double best_eff = -1.0;
+	for (int r = 12; r <= RMAX; ++r) {
+		const double n = (double)nx * ((band_rows + r - 1) / r);
+		const double waves = n / resident;
+		const double full = waves / (double)(long long)(waves + 0.999999);
+		const double eff = full * r / (r + 0.8);
+		if (eff > best_eff + 1e-9) { best_eff = eff; best = r; }
+	}
+	return best;
+}
+
+template <bool REJ, bool ALPHA, bool DIAG>
+cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const CUtensorMap& tmV, const CUtensorMap& tmD, unsigned int* fix_list, unsigned int* fix_count,
+                           unsigned int* fix_count_next, float band, int num_sms, cudaStream_t stream) {
+	auto kern = taa_resolve_stream_kernel<REJ, ALPHA, DIAG>;
+	const int smem = (int)sizeof(WarpSmem<REJ>) * NWARP;
+	static int resident_per_sm[64] = {0};  // per device (the attribute and the occupancy are per device)
+	int dev = 0;
+	cudaGetDevice(&dev);
+	dev &= 63;
+	if (!resident_per_sm[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e != cudaSuccess) return e;
+		cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100 * (REJ ? 6 : 8) * (smem + 1024) / (228 * 1024) + 2);
+		int nb = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * NWARP, smem);
+		if (e != cudaSuccess) return e;
+		resident_per_sm[dev] = nb > 0 ? nb : 1;
+	}
+	const int nstrips = (A.out_w + 1 + OWS - 1) / OWS;
+	const int nx = (nstrips + NWARP - 1) / NWARP;
+	const int R = pick_rows(nx, A.band_rows, resident_per_sm[dev] * num_sms);
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(nx, (A.band_rows + R - 1) / R);
+	cfg.blockDim = dim3(32 * NWARP);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kern, A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, R);
+}
+
+}  // namespace
+
+bool stream_supports(const ResolveArgs& A) {
+	static const bool off = [] { const char* v = getenv("TAA_TUNED_VARIANT"); return v && (v[0] == 's' || v[0] == 't'); }();  // "strip" / "tile": A/B partners
+	if (off || !encode_fn()) return false;
+	const TaaParameters& P = A.ubo.param[0];
+	if (!tma_able(A.color) || !tma_able(A.velocity)) return false;
+	if (P.mDepthCulling && !tma_able(A.depth)) return false;
+	return true;
+}
+
+cudaError_t launch_resolve_stream(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, bool fixup_all, int num_sms,
+                                  cudaStream_t stream) {
+	const float band = fixup_all ? INFINITY : FIXUP_BAND_4K * fmaxf(1.0f, fmaxf((float)A.out_w / 3840.0f, (float)A.out_h / 3840.0f));
+	const TaaParameters& P = A.ubo.param[0];
+	const bool rej = P.mDepthCulling || P.mRejectOutside || P.mDynamicAntiGhosting;
+	const bool alp = P.mVelBasedAlpha || P.mLumaWeightingLottes || P.mReduceBlendNearClamp;
+	const bool diag = fix_list != nullptr || A.mask.p != nullptr;
+	CUtensorMap tmC, tmV, tmD;
+	if (!make_map(&tmC, A.color, 2 * A.in_w, 2 * RWT) || !make_map(&tmV, A.velocity, 2 * A.in_w, 2 * RWT)) return cudaErrorInvalidValue;
+	if (rej && P.mDepthCulling) { if (!make_map(&tmD, A.depth, A.in_w, DW)) return cudaErrorInvalidValue; }
+	else tmD = tmC;
+#define TAA_STREAM_GO(RJ, AL, DG) return launch_variant<RJ, AL, DG>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream)
+	if (rej) { if (alp) TAA_STREAM_GO(true, true, true); TAA_STREAM_GO(true, false, true); }
+	if (diag) { if (alp) TAA_STREAM_GO(false, true, true); TAA_STREAM_GO(false, false, true); }
+	if (alp) TAA_STREAM_GO(false, true, false);
+	TAA_STREAM_GO(false, false, false);
+#undef TAA_STREAM_GO
+}
+
+}  // namespace taa

@@ -113,5 +113,60 @@ __device__ __forceinline__ HRow hfilter(const uint2 q0, const uint2 q1, const ui
 	return o;
 }
 
+// d = a * b + c with a, b fp16 and c, d fp32 (FHFMA): the product of two halves is exact in fp32
+__device__ __forceinline__ float fhfma(__half a, __half b, float c) {
+	float r;
+	asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r) : "h"(__half_as_ushort(a)), "h"(__half_as_ushort(b)), "f"(c));
+	return r;
+}
+
+// One sampled colour tap (taa.comp:207 through the sampler) converted to YCoCg: T[m] + px (T[nx] - T[m]) + py (T[ny] - T[m]).
+// px, py are ~1e-4 (the sampler coordinate lands that far beside the texel centre); the px*py cross term (< 1e-6) is dropped.
+__device__ __forceinline__ float3 sample_ycocg(const uint2 M, const uint2 NX, const uint2 NY, const __half px, const __half py) {
+	const __half2 m01 = h2(M.x), m23 = h2(M.y);
+	const __half2 dx01 = __hsub2(h2(NX.x), m01), dx23 = __hsub2(h2(NX.y), m23);
+	const __half2 dy01 = __hsub2(h2(NY.x), m01), dy23 = __hsub2(h2(NY.y), m23);
+	const float cr = fhfma(__low2half(dx01), px, fhfma(__low2half(dy01), py, __low2float(m01)));
+	const float cg = fhfma(__high2half(dx01), px, fhfma(__high2half(dy01), py, __high2float(m01)));
+	const float cb = fhfma(__low2half(dx23), px, fhfma(__low2half(dy23), py, __low2float(m23)));
+	const float t = cr + cb, hg = 0.5f * cg;
+	return make_float3(fmaf(0.25f, t, hg), 0.5f * (cr - cb), fmaf(-0.25f, t, hg));
+}
+
+// both halves of a packed pair are finite (exponent field != 31)
+__device__ __forceinline__ bool finite2(unsigned int v) { return (((v & 0x7c007c00u) + 0x04000400u) & 0x80008000u) == 0u; }
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned int)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+// ---- bulk (TMA) staging: one thread copies one whole tile row (544 bytes) global -> shared, completion counted on an mbarrier ----
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_row(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+	             "r"(smem_u32(bar)) : "memory");
+}
+
 }  // namespace tuned
 }  // namespace taa
