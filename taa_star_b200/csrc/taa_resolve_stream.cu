@@ -42,7 +42,7 @@ constexpr unsigned int ROWB = RWT * 8u;
 constexpr int SROWS = 2;                    // rows per slot = per TMA box
 constexpr int RMAX = 30;                    // output rows per unit: one 32-entry row table covers rows Y0 - 1 .. Y0 + 30
 constexpr int NWARP = 2;                    // warps (independent strips) per CTA
-constexpr int DW = 64;                      // depth ring row: columns Xs .. Xs + 63
+constexpr int DW = 80;                      // depth ring row: columns Xd .. Xd + 79, Xd = Xs rounded down to a multiple of four (a box starts on 16 bytes)
 constexpr unsigned int DROWB = DW * 4u;
 
 template <bool REJ>
@@ -59,7 +59,8 @@ struct __align__(128) WarpSmem {
 	unsigned char dt[REJ ? Cfg<REJ>::NR * DROWB : 128];  // depth rows, as colour
 	uint4 tabA[32];                                   // uniform motion: Catmull-Rom y weights of output row Y0 - 1 + t, permuted to the window's register order
 	uint4 tabB[32];                                   // output row: velocity footprint rows (ring offsets lo | hi << 16), weight, v, history v
-	uint4 tabC[32];                                   // sampled colour row: ring offsets m | n << 16, bleed weight (half bits); output row: (int)(hv * H), hv outside [0, 1)
+	uint4 tabC[32];                                   // x, y: sampled colour row: ring offsets m | n << 16, bleed weight (half bits); y bit 31, z: output row: hv outside [0, 1), (int)(hv * H);
+	                                                  // w: uniform motion: byte offset of the history row requested while output row t - 2 is evaluated
 	unsigned long long mbar[8];
 };
 
@@ -331,7 +332,7 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		mbar_expect_tx(bar, slot_bytes);
 		tma_load_2d(sm.craw + pos * (SROWS * ROWB), &tmC, 2 * Xb, Y0 - 2 + SROWS * k - A.color.y0, bar);
 		tma_load_2d(sm.vraw + pos * (SROWS * ROWB), &tmV, 2 * Xb, Y0 - 3 + SROWS * k - A.velocity.y0, bar);
-		if (use_depth) tma_load_2d(sm.dt + pos * (SROWS * DROWB), &tmD, Xs, Y0 - 2 + SROWS * k - A.depth.y0, bar);
+		if (use_depth) tma_load_2d(sm.dt + pos * (SROWS * DROWB), &tmD, Xs - (Xs & 3), Y0 - 2 + SROWS * k - A.depth.y0, bar);
 	};
 	auto wait_slot = [&](int k) { slot_wait(&sm.mbar[k % NSLOT], (unsigned int)((k / NSLOT) & 1)); };
 
@@ -405,36 +406,43 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	const uint2 vref = *reinterpret_cast<const uint2*>(sm.vraw + ring_row(Y0, Y0 - 3, NR) * ROWB + (unsigned int)(iclamp(Xs + 2, 0, W - 1) - Xb) * 8u);
 	bool uni = finite2(vref.x) && (!REJ || finite2(vref.y));
 	if (REJ && P.mDynamicAntiGhosting) uni = uni && (vref.y & 0x7fff0000u) == 0u;  // the strip's own motion is not a mover's
+	// velocity rows the unit samples that exist in the image must be in the buffer (else: general rows, which report them)
+	uni = uni && max(0, Y0 - 1 - LOOK) >= A.velocity.y0 && min(H - 1, Y0 + nr + LOOK) <= A.velocity.y0 + A.velocity.rows - 1;
 	unsigned int wrows = 0u;  // bit r: velocity row (newest voted - r) carries velocity.w != 0 somewhere under / beside the strip
-	auto vote_row = [&](int g) {
-		if (g < 0 || g > H - 1) return;
-		if (g < A.velocity.y0 || g >= A.velocity.y0 + A.velocity.rows) { uni = false; wrows = (wrows << 1) | 1u; return; }
-		const unsigned char* row = sm.vraw + ring_row(g, Y0 - 3, NR) * ROWB;
-		const uint4 t = *reinterpret_cast<const uint4*>(row + (unsigned int)(2 + 2 * lane) * 8u);
+	const unsigned char* vown = sm.vraw + (unsigned int)(2 + 2 * lane) * 8u;                                    // the lane's two texels in a ring row
+	const int cex = lane == 0 ? Xs - 1 : Xs + 64;                                                              // (rejection variants) the column beside the strip's outputs
+	const bool cev = REJ && (lane == 0 || lane == 31) && cex >= 0 && cex < W;
+	const unsigned char* vext = sm.vraw + (unsigned int)(iclamp(cex - Xb, 0, RWT - 1)) * 8u;
+	auto vote_row = [&](int g) -> bool {  // the lane's verdict on velocity row g (rows outside the image are never sampled as themselves)
+		if (g < 0 || g > H - 1) return true;
+		const unsigned int ro = ring_row(g, Y0 - 3, NR) * ROWB;
+		const uint4 t = *reinterpret_cast<const uint4*>(vown + ro);
 		bool ok = (!cv0 || (t.x == vref.x && (!REJ || t.y == vref.y))) && (!cv1 || (t.z == vref.x && (!REJ || t.w == vref.y)));
 		if (REJ) {
 			unsigned int wb = ((cv0 ? t.y : 0u) | (cv1 ? t.w : 0u)) & 0x7fff0000u;
-			if (lane == 0 || lane == 31) {  // columns Xs - 1 and Xs + 64: inside the 5 x 5 texels around the outermost outputs
-				const int ce = lane == 0 ? Xs - 1 : Xs + 64;
-				if (ce >= 0 && ce < W) {
-					const uint2 e = *reinterpret_cast<const uint2*>(row + (unsigned int)(ce - Xb) * 8u);
-					ok = ok && e.x == vref.x && e.y == vref.y;
-					wb |= e.y & 0x7fff0000u;
-				}
+			if (cev) {
+				const uint2 e = *reinterpret_cast<const uint2*>(vext + ro);
+				ok = ok && e.x == vref.x && e.y == vref.y;
+				wb |= e.y & 0x7fff0000u;
 			}
 			wrows = (wrows << 1) | (__any_sync(0xffffffffu, wb != 0u) ? 1u : 0u);
 		}
-		uni = uni && __all_sync(0xffffffffu, ok);
+		return ok;
 	};
-	if (REJ) { vote_row(Y0 - 2); vote_row(Y0 - 1); vote_row(Y0); vote_row(Y0 + 1); vote_row(Y0 + 2); }
-	else { vote_row(Y0 - 1); vote_row(Y0); }
+	{
+		bool ok = vote_row(Y0 - 1) & vote_row(Y0);
+		if (REJ) ok = ok & vote_row(Y0 - 2) & vote_row(Y0 + 1) & vote_row(Y0 + 2);
+		uni = uni && __all_sync(0xffffffffu, ok);
+	}
 
 	// ---- uniform motion: column constants and the motion-dependent part of the row tables ----
 	float wA[4] = {0.f, 0.f, 0.f, 0.f}, wB[4] = {0.f, 0.f, 0.f, 0.f};
 	float hu0 = 0.f, hu1 = 0.f, f_velz = 0.f;
 	int tx0 = 0, tx1 = 0;
 	bool outx0 = false, outx1 = false;
-	unsigned int hoff = 0u;  // byte offset of the history row in flight (first texel of the lane's five)
+	unsigned int oq[5] = {0u, 0u, 0u, 0u, 0u}, oe0 = 0u, oe1 = 0u;  // byte offsets in a history row: the lane's five texels (clamped to the image), alpha words beside them
+	int K0 = 0;                                                      // first footprint row of output row Y0
+	auto hrow = [&](int r) { return (unsigned int)(iclamp(r, 0, H - 1) - A.history_in.y0) * hpitch; };  // byte offset of history row r (clamp-to-edge)
 	if (uni) {
 		const float2 vxy = __half22float2(h2(vref.x));
 		if (REJ) f_velz = __low2float(h2(vref.y));
@@ -445,12 +453,15 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		for (int i = 0; i < 4; ++i) { wA[i] = a.w[i]; wB[i] = b.w[i]; }
 		tx0 = (int)(hu0 * fW); tx1 = (int)(hu1 * fW);
 		outx0 = hu0 < 0.f || hu0 >= 1.f; outx1 = hu1 < 0.f || hu1 >= 1.f;
-		const int rg = REJ ? 1 : 0;
-		bool ok = a.k - 1 - rg >= 0 && a.k + 3 + rg <= W - 1;
-		// rows: the footprint of output row Y0 + i starts at K0 + i
+#pragma unroll
+		for (int j = 0; j < 5; ++j) oq[j] = (unsigned int)iclamp(a.k - 1 + j, 0, W - 1) * 8u;
+		oe0 = (unsigned int)iclamp(a.k - 2, 0, W - 1) * 8u + 4u;
+		oe1 = (unsigned int)iclamp(a.k + 4, 0, W - 1) * 8u + 4u;
+		// rows: the footprint of output row Y0 + i starts at K0 + i; rows outside the image are clamped to its edge, the rest must be in the buffer
 		const float v_first = ((float)Y0 + 0.5f) / fH;
-		const int K0 = catmull_axis(v_first - vxy.y, fH, invh).k - 1;
-		ok = ok && K0 - rg >= hlo && K0 + nr + 2 + rg <= hhi;
+		K0 = catmull_axis(v_first - vxy.y, fH, invh).k - 1;
+		const int rg = REJ ? 1 : 0;
+		uni = iclamp(K0 - rg, 0, H - 1) >= hlo && iclamp(K0 + nr + 3, 0, H - 1) <= hhi;
 		const int g = Y0 - 1 + lane, i = lane - 1;
 		const float v = ((float)g + 0.5f) / fH;
 		const float hv = v - vxy.y;
@@ -461,11 +472,10 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		tb.w = __float_as_uint(hv);
 		sm.tabB[lane] = tb;
 		uint4 tc = sm.tabC[lane];
+		tc.y |= (hv < 0.f || hv >= 1.f) ? 0x80000000u : 0u;
 		tc.z = (unsigned int)(int)(hv * fH);
-		tc.w = (hv < 0.f || hv >= 1.f) ? 1u : 0u;
+		tc.w = hrow(K0 + lane + 2);  // entry t is read while output row t - 2 is evaluated: the row that joins the window then is K0 + (t - 2) + 4
 		sm.tabC[lane] = tc;
-		uni = __all_sync(0xffffffffu, ok);
-		hoff = (unsigned int)(K0 - A.history_in.y0) * hpitch + (unsigned int)(a.k - 1) * 8u;
 	}
 	__syncwarp();
 
@@ -473,7 +483,7 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	const unsigned char* cr = sm.craw;
 	auto sample_pair = [&](const uint4 tc, F3& a, F3& b) {
 		const unsigned int cm = tc.x & 0xffffu, cn = tc.x >> 16;
-		const __half py = __ushort_as_half((unsigned short)tc.y);
+		const __half py = __ushort_as_half((unsigned short)(tc.y & 0xffffu));
 		const float3 va = sample_ycocg(*reinterpret_cast<const uint2*>(cr + (cm + cm0)), *reinterpret_cast<const uint2*>(cr + (cm + cn0)),
 		                               *reinterpret_cast<const uint2*>(cr + (cn + cm0)), px0, py);
 		const float3 vb = sample_ycocg(*reinterpret_cast<const uint2*>(cr + (cm + cm1)), *reinterpret_cast<const uint2*>(cr + (cm + cn1)),
@@ -559,8 +569,8 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		const int k = i / 2 + 2 + LOOK;
 		if (k < nslots) {
 			wait_slot(k);
-			vote_row(Y0 + i + 1 + 2 * LOOK);
-			vote_row(Y0 + i + 2 + 2 * LOOK);
+			const bool ok = vote_row(Y0 + i + 1 + 2 * LOOK) & vote_row(Y0 + i + 2 + 2 * LOOK);
+			uni = uni && __all_sync(0xffffffffu, ok);
 		}
 	};
 	// end it: ring rows (Y0 - 2) + i + 2, + 3 are consumed, their slot is re-armed with the rows NSLOT slots further down
@@ -577,22 +587,25 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		HR hA[4], hB[4];
 		unsigned int orw[4] = {0u, 0u, 0u, 0u}, or_prev = 0u;  // OR of the alpha words of the window's rows / of the row above it (columns k - 2 .. k + 4)
 		{
-			const unsigned char* p = hbase + hoff;
 			if (REJ) {
-				const unsigned int* a = reinterpret_cast<const unsigned int*>(p - hpitch - 4);
-				or_prev = (__ldg(a) | __ldg(a + 2) | __ldg(a + 4)) | (__ldg(a + 6) | __ldg(a + 8) | __ldg(a + 10)) | __ldg(a + 12);
+				const unsigned char* p = hbase + hrow(K0 - 1) + 4;
+				or_prev = (__ldg(reinterpret_cast<const unsigned int*>(p + oq[0])) | __ldg(reinterpret_cast<const unsigned int*>(p + oq[1])) |
+				           __ldg(reinterpret_cast<const unsigned int*>(p + oq[2]))) |
+				          (__ldg(reinterpret_cast<const unsigned int*>(p + oq[3])) | __ldg(reinterpret_cast<const unsigned int*>(p + oq[4]))) |
+				          (__ldg(reinterpret_cast<const unsigned int*>(p - 4 + oe0)) | __ldg(reinterpret_cast<const unsigned int*>(p - 4 + oe1)));
 			}
 #pragma unroll
 			for (int j = 0; j < 4; ++j) {
-				const uint2* hp = reinterpret_cast<const uint2*>(p + j * hpitch);
-				const uint2 q0 = __ldg(hp), q1 = __ldg(hp + 1), q2 = __ldg(hp + 2), q3 = __ldg(hp + 3), q4 = __ldg(hp + 4);
+				const unsigned char* p = hbase + hrow(K0 + j);
+				const uint2 q0 = __ldg(reinterpret_cast<const uint2*>(p + oq[0])), q1 = __ldg(reinterpret_cast<const uint2*>(p + oq[1])),
+				            q2 = __ldg(reinterpret_cast<const uint2*>(p + oq[2])), q3 = __ldg(reinterpret_cast<const uint2*>(p + oq[3])),
+				            q4 = __ldg(reinterpret_cast<const uint2*>(p + oq[4]));
 				if (REJ) {
-					const unsigned int e0 = __ldg(reinterpret_cast<const unsigned int*>(p + j * hpitch - 4)), e1 = __ldg(reinterpret_cast<const unsigned int*>(p + j * hpitch + 44));
+					const unsigned int e0 = __ldg(reinterpret_cast<const unsigned int*>(p + oe0)), e1 = __ldg(reinterpret_cast<const unsigned int*>(p + oe1));
 					orw[j] = (q0.y | q1.y | q2.y) | (q3.y | q4.y) | (e0 | e1);
 				}
 				hfilter_pair<REJ>(q0, q1, q2, q3, q4, wA, wB, hA[j], hB[j]);
 			}
-			hoff += 4u * hpitch;
 		}
 		float hdA = 0.f, hdB = 0.f;  // previous depth at the history position of the next pixel row (requested one row ahead)
 		if (use_depth) {
@@ -605,21 +618,17 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		auto fast_row = [&](auto PHC, const int i) {
 			constexpr int PH = decltype(PHC)::value;  // the register slot the row in flight replaces: i & 3
 			const int t = i + 1;
-			// the history row the next pixel row adds: K0 + i + 4
-			uint2 q0 = make_uint2(0u, 0u), q1 = q0, q2 = q0, q3 = q0, q4 = q0;
+			// the history row the next pixel row adds, K0 + i + 4, is requested now and consumed at the end of this row
+			const uint4 tcn = sm.tabC[t + 1];
+			const unsigned char* p = hbase + tcn.w;
+			const uint2 q0 = __ldg(reinterpret_cast<const uint2*>(p + oq[0])), q1 = __ldg(reinterpret_cast<const uint2*>(p + oq[1])),
+			            q2 = __ldg(reinterpret_cast<const uint2*>(p + oq[2])), q3 = __ldg(reinterpret_cast<const uint2*>(p + oq[3])),
+			            q4 = __ldg(reinterpret_cast<const uint2*>(p + oq[4]));
 			unsigned int e0 = 0u, e1 = 0u;
-			const bool ahead = REJ || i + 1 < nr;
-			if (ahead) {
-				const unsigned char* p = hbase + hoff;
-				const uint2* hp = reinterpret_cast<const uint2*>(p);
-				q0 = __ldg(hp); q1 = __ldg(hp + 1); q2 = __ldg(hp + 2); q3 = __ldg(hp + 3); q4 = __ldg(hp + 4);
-				if (REJ) {
-					e0 = __ldg(reinterpret_cast<const unsigned int*>(p - 4));
-					e1 = __ldg(reinterpret_cast<const unsigned int*>(p + 44));
-				}
+			if (REJ) {
+				e0 = __ldg(reinterpret_cast<const unsigned int*>(p + oe0));
+				e1 = __ldg(reinterpret_cast<const unsigned int*>(p + oe1));
 			}
-			hoff += hpitch;
-			if (i + 2 < nr) asm volatile("prefetch.global.L1 [%0];" ::"l"(hbase + (hoff + ((lane & 1) ? 32u : 0u))));  // the row after it
 			float hdA_n = 0.f, hdB_n = 0.f;
 			if (use_depth && i + 1 < nr) {
 				const int ty = (int)sm.tabC[t + 1].z;
@@ -630,7 +639,7 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 			const float wy0 = __uint_as_float(wyu.x), wy1 = __uint_as_float(wyu.y), wy2 = __uint_as_float(wyu.z), wy3 = __uint_as_float(wyu.w);
 			// sampled row y + 1 joins the rolling box
 			F3 S1a, S2a, S1b, S2b;
-			advance_box(std::integral_constant<int, PH & 1>{}, sm.tabC[t + 1], S1a, S2a, S1b, S2b);
+			advance_box(std::integral_constant<int, PH & 1>{}, tcn, S1a, S2a, S1b, S2b);
 			// the footprints, filtered vertically
 			const float ar = fmaf(wy3, hA[3].r, fmaf(wy2, hA[2].r, fmaf(wy1, hA[1].r, wy0 * hA[0].r)));
 			const float ag = fmaf(wy3, hA[3].g, fmaf(wy2, hA[2].g, fmaf(wy1, hA[1].g, wy0 * hA[0].g)));
@@ -652,9 +661,9 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 			}
 			if (REJ) {
 				const uint4 tc = sm.tabC[t];
-				if (P.mRejectOutside) { rejA = outx0 || tc.w != 0u; rejB = outx1 || tc.w != 0u; }
+				if (P.mRejectOutside) { rejA = outx0 || (tc.y >> 31) != 0u; rejB = outx1 || (tc.y >> 31) != 0u; }
 				if (use_depth) {
-					const float2 d = *reinterpret_cast<const float2*>(sm.dt + ring_row(Y0 + i, Y0 - 2, NR) * DROWB + (unsigned int)lane * 8u);
+					const float2 d = *reinterpret_cast<const float2*>(sm.dt + ring_row(Y0 + i, Y0 - 2, NR) * DROWB + (unsigned int)(2 * lane + (Xs & 3)) * 4u);
 					const float ea = d.x - f_velz, eb = d.y - f_velz;
 					if (fabsf(hdA - ea) > 0.1f * (1.0f - hdA)) rejA = true;
 					if (fabsf(hdB - eb) > 0.1f * (1.0f - hdB)) rejB = true;
@@ -765,24 +774,26 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 			if (REJ && o.check_ring && (ring & 0x7fff0000u)) o.uncertain = true;
 			return o;
 		};
-		auto general_row = [&](auto EC, const int i) {
-			constexpr int E = decltype(EC)::value;  // parity of the unit row
+		auto general_row = [&](const int i) {  // (the rolling box is kept in slot 0: the general rows move it there, a few MOVs do not matter here)
 			const int t = i + 1;
 			F3 S1a, S2a, S1b, S2b;
-			advance_box(EC, sm.tabC[t + 1], S1a, S2a, S1b, S2b);
+			advance_box(std::integral_constant<int, 0>{}, sm.tabC[t + 1], S1a, S2a, S1b, S2b);
+			const F3 ca = CURA[0], cb = CURB[0];
+			QA[0] = QA[1]; QB[0] = QB[1]; CURA[0] = CURA[1]; CURB[0] = CURB[1];
 			float2 d = make_float2(0.f, 0.f);
-			if (use_depth) d = *reinterpret_cast<const float2*>(sm.dt + ring_row(Y0 + i, Y0 - 2, NR) * DROWB + (unsigned int)lane * 8u);
+			if (use_depth) d = *reinterpret_cast<const float2*>(sm.dt + ring_row(Y0 + i, Y0 - 2, NR) * DROWB + (unsigned int)(2 * lane + (Xs & 3)) * 4u);
 			// velocity rows up to Y0 + i + 4 (+ 1) have been voted: bits 0 .. 7 cover rows y - 2 .. y + 2 of both rows of the step
 			const bool movers_near = REJ && (wrows & 0xffu) != 0u;
-			const PixOut oa = general_pixel(i, vo00, vo01, va0, u0, CURA[E], S1a, S2a, d.x, movers_near);
-			const PixOut ob = general_pixel(i, vo10, vo11, va1, u1, CURB[E], S1b, S2b, d.y, movers_near);
+			const PixOut oa = general_pixel(i, vo00, vo01, va0, u0, ca, S1a, S2a, d.x, movers_near);
+			const PixOut ob = general_pixel(i, vo10, vo11, va1, u1, cb, S1b, S2b, d.y, movers_near);
 			store_row(oa, ob, i);
 		};
+		if (i & 1) { QA[0] = QA[1]; QB[0] = QB[1]; CURA[0] = CURA[1]; CURB[0] = CURB[1]; }  // (never: the uniform rows are left at a step boundary)
 		while (i < nr) {
 			if (!begun) step_begin(i);
 			begun = false;
-			general_row(std::integral_constant<int, 0>{}, i);
-			if (i + 1 < nr) general_row(std::integral_constant<int, 1>{}, i + 1);
+			general_row(i);
+			if (i + 1 < nr) general_row(i + 1);
 			step_end(i);
 			i += 2;
 		}
