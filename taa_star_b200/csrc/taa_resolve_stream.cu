@@ -167,6 +167,20 @@ __device__ __forceinline__ void hfilter_pair(const uint2 q0, const uint2 q1, con
 	}
 }
 
+// The switches of `Parameters` the family leaves open. FX = 0: read from the parameter block (warp-uniform branches); FX = 1: the BASELINE
+// config 3 combination, fixed at compile time (reject outside + depth culling + dynamic anti-ghosting, velocity alpha + Lottes luma weighting,
+// no near-clamp reduction, no history reset) — the host picks the variant.
+template <int FX>
+struct Sw {
+	__device__ __forceinline__ static bool outside(const TaaParameters& P) { return FX ? true : P.mRejectOutside != 0; }
+	__device__ __forceinline__ static bool depth(const TaaParameters& P) { return FX ? true : P.mDepthCulling != 0; }
+	__device__ __forceinline__ static bool antighost(const TaaParameters& P) { return FX ? true : P.mDynamicAntiGhosting != 0; }
+	__device__ __forceinline__ static bool velalpha(const TaaParameters& P) { return FX ? true : P.mVelBasedAlpha != 0; }
+	__device__ __forceinline__ static bool lottes(const TaaParameters& P) { return FX ? true : P.mLumaWeightingLottes != 0; }
+	__device__ __forceinline__ static bool nearclamp(const TaaParameters& P) { return FX ? false : P.mReduceBlendNearClamp != 0; }
+	__device__ __forceinline__ static bool reset(const TaaUniforms& U) { return FX ? false : U.mResetHistory != 0; }
+};
+
 // warp-uniform constants of a dispatch
 struct KConst {
 	float gg9, rg9, tiny;  // gamma^2 / 9 (at least 1e-12), its inverse square root, 1e-14 / gg9
@@ -183,7 +197,7 @@ struct PixOut {
 // Everything of taa.comp::main after the history sample (taa.comp:769-909) for one pixel. cur = sampled current colour (YCoCg), S1 / S2 =
 // sum and sum of squares over the 3 x 3 neighbourhood, hs* = filtered history (rgb, alpha), rejected = outside / depth decisions of the
 // caller (exact predicates), movement / movC = the 5-tap velocity test and its centre tap, du / dv = uv - history uv.
-template <bool REJ, bool ALPHA, bool DIAG>
+template <bool REJ, bool ALPHA, bool DIAG, int FX>
 __device__ __forceinline__ PixOut resolve_pixel(const ResolveArgs& A, const KConst& kc, const float fix_band, const F3 cur, const F3 S1, const F3 S2, const float hsr,
                                                 const float hsg, const float hsb, const float hsa, bool rejected, const bool movement, const bool movC, const float du,
                                                 const float dv) {
@@ -203,7 +217,7 @@ __device__ __forceinline__ PixOut resolve_pixel(const ResolveArgs& A, const KCon
 	const float hx = fmaf(0.25f, t, hg2), hy = 0.5f * (hsr - hsb), hz = fmaf(-0.25f, t, hg2);
 	// ---- rejection by history alpha (taa.comp:796-811)
 	float wdm = 0.f;
-	if (REJ && P.mDynamicAntiGhosting) {
+	if (REJ && Sw<FX>::antighost(P)) {
 		if (!movement) {
 			if (hsa > 0.0f) rejected = true;
 			// the sign of a filtered 0/1 mask that cancels to ~0 is not safe under re-association: undecided if the 6x6 ring carries alpha at all
@@ -225,18 +239,19 @@ __device__ __forceinline__ PixOut resolve_pixel(const ResolveArgs& A, const KCon
 	}
 	// ---- blend (taa.comp:848-900)
 	float alpha = kc.alpha0;
-	if (REJ && rejected) alpha = kc.reset ? 1.0f : P.mRejectionAlpha;
-	else if (ALPHA && !kc.reset) {
-		if (P.mVelBasedAlpha) {
+	const bool reset = FX ? false : kc.reset;
+	if (REJ && rejected) alpha = reset ? 1.0f : P.mRejectionAlpha;
+	else if (ALPHA && !reset) {
+		if (Sw<FX>::velalpha(P)) {
 			const float speed = sqrt_approx(fmaf(du, du, dv * dv));
 			alpha = fmaxf(alpha, mixf(alpha, P.mVelBasedAlphaMax, sat(speed * P.mVelBasedAlphaFactor)));
 		}
-		if (P.mLumaWeightingLottes) {
+		if (Sw<FX>::lottes(P)) {
 			const float lc = cur.x, lh = cx;
 			const float w = 1.0f - fabsf(lc - lh) * rcp_approx(fmaxf(fmaxf(lc, lh), 0.2f));
 			alpha = mixf(P.mMaxAlpha, P.mMinAlpha, w * w);
 		}
-		if (P.mReduceBlendNearClamp) {
+		if (Sw<FX>::nearclamp(P)) {
 			const float ex = (kc.gg9 * fmaxf(e2x, 0.f)) * (ix * kc.rg9);  // the extent of the luma axis: sqrt(gg9 e2)
 			const float lmin = mx - ex, lmax = mx + ex, lh = hx;
 			float dist = 2.0f * fabsf(fminf(lh - lmin, lmax - lh)) * rcp_approx(lmax - lmin);
@@ -299,11 +314,11 @@ __device__ __forceinline__ void gather_history(const ResolveArgs& A, const float
 	hsa = REJ ? fmaf(ay.w[3], r3.a, fmaf(ay.w[2], r2.a, fmaf(ay.w[1], r1.a, ay.w[0] * r0.a))) : 0.f;
 }
 
-template <bool REJ, bool ALPHA, bool DIAG>
-__global__ void __launch_bounds__(32 * NWARP, REJ ? 6 : 8)
+template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB>
+__global__ void __launch_bounds__(32 * NWARP, MINB)
 taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmV,
                           const __grid_constant__ CUtensorMap tmD, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
-                          unsigned int* __restrict__ fix_count_next, const float fix_band, const int R) {
+                          unsigned int* __restrict__ fix_count_next, const float fix_band, const int R, const unsigned int rt_zero) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	using C = Cfg<REJ>;
 	constexpr int NSLOT = C::NSLOT, NR = C::NR, LOOK = C::LOOK;
@@ -323,7 +338,7 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && fix_count_next) *fix_count_next = 0u;  // the counter the next frame appends to
 	if (Xs + 1 > W - 1 || nr <= 0) return;  // (warp-uniform; there is no block-wide barrier in this kernel)
 
-	const bool use_depth = REJ && P.mDepthCulling;
+	const bool use_depth = REJ && Sw<FX>::depth(P);
 	const int nslots = (nr + 4 + LOOK + 1) / 2;  // ring rows Y0 - 2 .. Y0 + nr + 1 (+ LOOK) in boxes of two
 	const unsigned int slot_bytes = 2u * SROWS * ROWB + (use_depth ? SROWS * DROWB : 0u);
 	auto issue = [&](int k) {  // lane 0: arm slot k and request its boxes
@@ -368,7 +383,7 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		kc.gg9 = fmaxf(P.mVarClipGamma * P.mVarClipGamma * (1.0f / 9.0f), 1e-12f);
 		kc.rg9 = rsqrt_approx(kc.gg9);
 		kc.tiny = 1e-14f * rcp_approx(kc.gg9);
-		kc.reset = A.ubo.mResetHistory != 0;
+		kc.reset = Sw<FX>::reset(A.ubo);
 		kc.alpha0 = kc.reset ? 1.0f : P.mAlpha;
 	}
 	const int hlo = max(0, A.history_in.y0), hhi = min(H - 1, A.history_in.y0 + A.history_in.rows - 1);
@@ -405,7 +420,7 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	// does not hold end the uniform path (the general rows report them).
 	const uint2 vref = *reinterpret_cast<const uint2*>(sm.vraw + ring_row(Y0, Y0 - 3, NR) * ROWB + (unsigned int)(iclamp(Xs + 2, 0, W - 1) - Xb) * 8u);
 	bool uni = finite2(vref.x) && (!REJ || finite2(vref.y));
-	if (REJ && P.mDynamicAntiGhosting) uni = uni && (vref.y & 0x7fff0000u) == 0u;  // the strip's own motion is not a mover's
+	if (REJ && Sw<FX>::antighost(P)) uni = uni && (vref.y & 0x7fff0000u) == 0u;  // the strip's own motion is not a mover's
 	// velocity rows the unit samples that exist in the image must be in the buffer (else: general rows, which report them)
 	uni = uni && max(0, Y0 - 1 - LOOK) >= A.velocity.y0 && min(H - 1, Y0 + nr + LOOK) <= A.velocity.y0 + A.velocity.rows - 1;
 	unsigned int wrows = 0u;  // bit r: velocity row (newest voted - r) carries velocity.w != 0 somewhere under / beside the strip
@@ -621,9 +636,9 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 			// the history row the next pixel row adds, K0 + i + 4, is requested now and consumed at the end of this row
 			const uint4 tcn = sm.tabC[t + 1];
 			const unsigned char* p = hbase + tcn.w;
-			const uint2 q0 = __ldg(reinterpret_cast<const uint2*>(p + oq[0])), q1 = __ldg(reinterpret_cast<const uint2*>(p + oq[1])),
-			            q2 = __ldg(reinterpret_cast<const uint2*>(p + oq[2])), q3 = __ldg(reinterpret_cast<const uint2*>(p + oq[3])),
-			            q4 = __ldg(reinterpret_cast<const uint2*>(p + oq[4]));
+			uint2 q0 = __ldg(reinterpret_cast<const uint2*>(p + oq[0])), q1 = __ldg(reinterpret_cast<const uint2*>(p + oq[1])),
+			      q2 = __ldg(reinterpret_cast<const uint2*>(p + oq[2])), q3 = __ldg(reinterpret_cast<const uint2*>(p + oq[3])),
+			      q4 = __ldg(reinterpret_cast<const uint2*>(p + oq[4]));
 			unsigned int e0 = 0u, e1 = 0u;
 			if (REJ) {
 				e0 = __ldg(reinterpret_cast<const unsigned int*>(p + oe0));
@@ -661,7 +676,7 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 			}
 			if (REJ) {
 				const uint4 tc = sm.tabC[t];
-				if (P.mRejectOutside) { rejA = outx0 || (tc.y >> 31) != 0u; rejB = outx1 || (tc.y >> 31) != 0u; }
+				if (Sw<FX>::outside(P)) { rejA = outx0 || (tc.y >> 31) != 0u; rejB = outx1 || (tc.y >> 31) != 0u; }
 				if (use_depth) {
 					const float2 d = *reinterpret_cast<const float2*>(sm.dt + ring_row(Y0 + i, Y0 - 2, NR) * DROWB + (unsigned int)(2 * lane + (Xs & 3)) * 4u);
 					const float ea = d.x - f_velz, eb = d.y - f_velz;
@@ -669,9 +684,18 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 					if (fabsf(hdB - eb) > 0.1f * (1.0f - hdB)) rejB = true;
 				}
 			}
-			PixOut oa = resolve_pixel<REJ, ALPHA, DIAG>(A, kc, fix_band, CURA[PH & 1], S1a, S2a, ar, ag, ab, aa, rejA, false, false, u0 - hu0, dv);
-			PixOut ob = resolve_pixel<REJ, ALPHA, DIAG>(A, kc, fix_band, CURB[PH & 1], S1b, S2b, br, bg, bb, ba, rejB, false, false, u1 - hu1, dv);
-			// slide the window: the row that was in flight replaces the oldest
+			PixOut oa = resolve_pixel<REJ, ALPHA, DIAG, FX>(A, kc, fix_band, CURA[PH & 1], S1a, S2a, ar, ag, ab, aa, rejA, false, false, u0 - hu0, dv);
+			PixOut ob = resolve_pixel<REJ, ALPHA, DIAG, FX>(A, kc, fix_band, CURB[PH & 1], S1b, S2b, br, bg, bb, ba, rejB, false, false, u1 - hu1, dv);
+			// slide the window: the row that was in flight replaces the oldest. The texels are not to be touched (= waited for) any earlier:
+			// left alone, ptxas packs the blue halves of the five texels into spare register halves right behind the loads to save registers, and
+			// the look-ahead is gone (ncu: 40 % of the stall samples sat on those PRMTs).
+			// What keeps them: the second word of each texel is XORed with a zero that exists only once the row's colours do (rt_zero is a kernel
+			// argument that is always 0; ptxas cannot know).
+			if (!REJ) {
+				store_row(oa, ob, i);
+				const unsigned int z = (oa.rg ^ ob.bh) & rt_zero;
+				q0.y ^= z; q1.y ^= z; q2.y ^= z; q3.y ^= z; q4.y ^= z;
+			}
 			if (REJ) {
 				const unsigned int or_new = (q0.y | q1.y | q2.y) | (q3.y | q4.y) | (e0 | e1);
 				if ((oa.check_ring || ob.check_ring) && (((or_prev | or_new) | (orw[0] | orw[1]) | (orw[2] | orw[3])) & 0x7fff0000u)) {
@@ -681,8 +705,8 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 				or_prev = orw[PH];
 				orw[PH] = or_new;
 				hdA = hdA_n; hdB = hdB_n;
+				store_row(oa, ob, i);
 			}
-			store_row(oa, ob, i);
 			hfilter_pair<REJ>(q0, q1, q2, q3, q4, wA, wB, hA[PH], hB[PH]);
 		};
 
@@ -750,8 +774,8 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 			gather_history<REJ>(A, hu, hv, W, H, fW, fH, invw, invh, hlo, hhi, hsr, hsg, hsb, hsa, ring);
 			bool rejected = false, movement = false;
 			if (REJ) {
-				if (P.mRejectOutside && (hu < 0.f || hv < 0.f || hu >= 1.f || hv >= 1.f)) rejected = true;
-				if (P.mDynamicAntiGhosting) {
+				if (Sw<FX>::outside(P) && (hu < 0.f || hv < 0.f || hu >= 1.f || hv >= 1.f)) rejected = true;
+				if (Sw<FX>::antighost(P)) {
 					movement = movC;
 					// the four other taps of the movement test (taa.comp:796-806): where no texel within two of the strip's recent rows carries
 					// velocity.w, every tap's w is exactly 0
@@ -764,13 +788,13 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 						           mov(u + invw * 0.f, v + invh * 1.f);
 					}
 				}
-				if (P.mDepthCulling) {
+				if (use_depth) {
 					const float expected = depth - velz;
 					const float hd = fetch_r32f(A.history_depth, W, H, (int)(hu * fW), (int)(hv * fH), st);
 					if (fabsf(hd - expected) > 0.1f * (1.0f - hd)) rejected = true;
 				}
 			}
-			PixOut o = resolve_pixel<REJ, ALPHA, DIAG>(A, kc, fix_band, cur, S1, S2, hsr, hsg, hsb, hsa, rejected, movement, movC, u - hu, v - hv);
+			PixOut o = resolve_pixel<REJ, ALPHA, DIAG, FX>(A, kc, fix_band, cur, S1, S2, hsr, hsg, hsb, hsa, rejected, movement, movC, u - hu, v - hv);
 			if (REJ && o.check_ring && (ring & 0x7fff0000u)) o.uncertain = true;
 			return o;
 		};
@@ -871,10 +895,10 @@ int pick_rows(int nx, int band_rows, int resident) {
 	return best;
 }
 
-template <bool REJ, bool ALPHA, bool DIAG>
+template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB>
 cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const CUtensorMap& tmV, const CUtensorMap& tmD, unsigned int* fix_list, unsigned int* fix_count,
                            unsigned int* fix_count_next, float band, int num_sms, cudaStream_t stream) {
-	auto kern = taa_resolve_stream_kernel<REJ, ALPHA, DIAG>;
+	auto kern = taa_resolve_stream_kernel<REJ, ALPHA, DIAG, FX, MINB>;
 	const int smem = (int)sizeof(WarpSmem<REJ>) * NWARP;
 	static int resident_per_sm[64] = {0};  // per device (the attribute and the occupancy are per device)
 	int dev = 0;
@@ -883,7 +907,7 @@ cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const C
 	if (!resident_per_sm[dev]) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e != cudaSuccess) return e;
-		cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100 * (REJ ? 6 : 8) * (smem + 1024) / (228 * 1024) + 2);
+		cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100 * MINB * (smem + 1024) / (228 * 1024) + 2);
 		int nb = 0;
 		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * NWARP, smem);
 		if (e != cudaSuccess) return e;
@@ -902,7 +926,7 @@ cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const C
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
-	return cudaLaunchKernelEx(&cfg, kern, A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, R);
+	return cudaLaunchKernelEx(&cfg, kern, A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, R, 0u);
 }
 
 }  // namespace
@@ -927,11 +951,21 @@ cudaError_t launch_resolve_stream(const ResolveArgs& A, unsigned int* fix_list, 
 	if (!make_map(&tmC, A.color, 2 * A.in_w, 2 * RWT) || !make_map(&tmV, A.velocity, 2 * A.in_w, 2 * RWT)) return cudaErrorInvalidValue;
 	if (rej && P.mDepthCulling) { if (!make_map(&tmD, A.depth, A.in_w, DW)) return cudaErrorInvalidValue; }
 	else tmD = tmC;
-#define TAA_STREAM_GO(RJ, AL, DG) return launch_variant<RJ, AL, DG>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream)
-	if (rej) { if (alp) TAA_STREAM_GO(true, true, true); TAA_STREAM_GO(true, false, true); }
-	if (diag) { if (alp) TAA_STREAM_GO(false, true, true); TAA_STREAM_GO(false, false, true); }
-	if (alp) TAA_STREAM_GO(false, true, false);
-	TAA_STREAM_GO(false, false, false);
+	// Resident CTAs per SM (= the register budget): the A/B on B200 decides the defaults; TAA_STREAM_MINB overrides (tuning aid).
+	static const int minb_env = [] { const char* v = getenv("TAA_STREAM_MINB"); return v ? atoi(v) : 0; }();
+	const bool fx3 = rej && alp && P.mDepthCulling && P.mRejectOutside && P.mDynamicAntiGhosting && P.mVelBasedAlpha && P.mLumaWeightingLottes &&
+	                 !P.mReduceBlendNearClamp && !A.ubo.mResetHistory;
+#define TAA_STREAM_GO(RJ, AL, DG, FX, MB) return launch_variant<RJ, AL, DG, FX, MB>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream)
+	if (rej) {
+		if (fx3) { if (minb_env == 4) TAA_STREAM_GO(true, true, true, 1, 4); if (minb_env == 5) TAA_STREAM_GO(true, true, true, 1, 5); TAA_STREAM_GO(true, true, true, 1, 6); }
+		if (alp) TAA_STREAM_GO(true, true, true, 0, 6);
+		TAA_STREAM_GO(true, false, true, 0, 6);
+	}
+	if (diag) { if (alp) TAA_STREAM_GO(false, true, true, 0, 8); TAA_STREAM_GO(false, false, true, 0, 8); }
+	if (alp) TAA_STREAM_GO(false, true, false, 0, 8);
+	if (minb_env == 6) TAA_STREAM_GO(false, false, false, 0, 6);
+	if (minb_env == 7) TAA_STREAM_GO(false, false, false, 0, 7);
+	TAA_STREAM_GO(false, false, false, 0, 8);
 #undef TAA_STREAM_GO
 }
 
