@@ -42,6 +42,7 @@ constexpr unsigned int ROWB = RWT * 8u;
 constexpr int SROWS = 2;                    // rows per slot = per TMA box
 constexpr int RMAX = 30;                    // output rows per unit: one 32-entry row table covers rows Y0 - 1 .. Y0 + 30
 constexpr int NWARP = 2;                    // warps (independent strips) per CTA
+constexpr int PFD = 3;                      // L2 prefetch distance of the history rows, in rows beyond the one requested (0: off)
 constexpr int DW = 80;                      // depth ring row: columns Xd .. Xd + 79, Xd = Xs rounded down to a multiple of four (a box starts on 16 bytes)
 constexpr unsigned int DROWB = DW * 4u;
 
@@ -455,6 +456,8 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	float hu0 = 0.f, hu1 = 0.f, f_velz = 0.f;
 	int tx0 = 0, tx1 = 0;
 	bool outx0 = false, outx1 = false;
+	const unsigned int hmax_off = (unsigned int)(hhi - A.history_in.y0) * hpitch;  // last history row that is both in the image and in the buffer
+	unsigned int pf_off = 0u;                                        // lanes 0 .. 5: the 128-byte lines of the strip's history row segment, PFD rows further down
 	unsigned int oq[5] = {0u, 0u, 0u, 0u, 0u}, oe0 = 0u, oe1 = 0u;  // byte offsets in a history row: the lane's five texels (clamped to the image), alpha words beside them
 	int K0 = 0;                                                      // first footprint row of output row Y0
 	auto hrow = [&](int r) { return (unsigned int)(iclamp(r, 0, H - 1) - A.history_in.y0) * hpitch; };  // byte offset of history row r (clamp-to-edge)
@@ -472,6 +475,10 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		for (int j = 0; j < 5; ++j) oq[j] = (unsigned int)iclamp(a.k - 1 + j, 0, W - 1) * 8u;
 		oe0 = (unsigned int)iclamp(a.k - 2, 0, W - 1) * 8u + 4u;
 		oe1 = (unsigned int)iclamp(a.k + 4, 0, W - 1) * 8u + 4u;
+		{
+			const unsigned int first = __shfl_sync(0xffffffffu, oq[0], 0);  // lane 0's first texel: the segment starts there (or a few texels further left at the image border)
+			pf_off = min((first & ~127u) + 128u * (unsigned int)lane, (unsigned int)(W - 1) * 8u);
+		}
 		// rows: the footprint of output row Y0 + i starts at K0 + i; rows outside the image are clamped to its edge, the rest must be in the buffer
 		const float v_first = ((float)Y0 + 0.5f) / fH;
 		K0 = catmull_axis(v_first - vxy.y, fH, invh).k - 1;
@@ -482,7 +489,12 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		const float hv = v - vxy.y;
 		const AxisW wy = catmull_axis_k(hv, fH, invh, (float)(K0 + 1 + i));
 		// the window keeps history row K0 + i + j in register slot (i + j) & 3: slot p carries weight (p - i) & 3
-		sm.tabA[lane] = make_uint4(__float_as_uint(wy.w[(0 - i) & 3]), __float_as_uint(wy.w[(1 - i) & 3]), __float_as_uint(wy.w[(2 - i) & 3]), __float_as_uint(wy.w[(3 - i) & 3]));
+		{
+			const int r = i & 3;  // rotate the four weights by r positions (selects: an indexed register array would live in local memory)
+			const float a0 = (r & 1) ? wy.w[3] : wy.w[0], a1 = (r & 1) ? wy.w[0] : wy.w[1], a2 = (r & 1) ? wy.w[1] : wy.w[2], a3 = (r & 1) ? wy.w[2] : wy.w[3];
+			const float b0 = (r & 2) ? a2 : a0, b1 = (r & 2) ? a3 : a1, b2 = (r & 2) ? a0 : a2, b3 = (r & 2) ? a1 : a3;
+			sm.tabA[lane] = make_uint4(__float_as_uint(b0), __float_as_uint(b1), __float_as_uint(b2), __float_as_uint(b3));
+		}
 		uint4 tb = sm.tabB[lane];
 		tb.w = __float_as_uint(hv);
 		sm.tabB[lane] = tb;
@@ -644,6 +656,8 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 				e0 = __ldg(reinterpret_cast<const unsigned int*>(p + oe0));
 				e1 = __ldg(reinterpret_cast<const unsigned int*>(p + oe1));
 			}
+			// the rows further down are pulled into L2 meanwhile: one row of look-ahead covers an L2 hit, not a DRAM access under load
+			if (PFD > 0 && lane < 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(hbase + (min(tcn.w + (unsigned int)PFD * hpitch, hmax_off) + pf_off)));
 			float hdA_n = 0.f, hdB_n = 0.f;
 			if (use_depth && i + 1 < nr) {
 				const int ty = (int)sm.tabC[t + 1].z;
@@ -879,7 +893,7 @@ bool make_map(CUtensorMap* tm, const Img& im, int words_per_row, int box_w) {
 bool tma_able(const Img& im) { return im.p && (((unsigned long long)im.p | (unsigned long long)im.pitch) & 15ull) == 0ull && im.rows > 0; }
 
 // Rows per unit: the grid is (strip pairs) x ceil(band / R) CTAs on `resident` CTA slots; take the R whose last wave is fullest, weighted
-// by the per-unit overhead (two extra sampled rows, three extra history rows: ~0.8 of a row)
+// by the per-unit overhead (tables, two extra sampled rows, the first window: ~2.5 rows' worth of instructions)
 int pick_rows(int nx, int band_rows, int resident) {
 	static const int forced = [] { const char* s = getenv("TAA_STREAM_R"); return s ? atoi(s) : 0; }();
 	if (forced >= 2 && forced <= RMAX) return forced;
@@ -889,7 +903,7 @@ int pick_rows(int nx, int band_rows, int resident) {
 		const double n = (double)nx * ((band_rows + r - 1) / r);
 		const double waves = n / resident;
 		const double full = waves / (double)(long long)(waves + 0.999999);
-		const double eff = full * r / (r + 0.8);
+		const double eff = full * r / (r + 2.5);
 		if (eff > best_eff + 1e-9) { best_eff = eff; best = r; }
 	}
 	return best;
@@ -961,11 +975,11 @@ cudaError_t launch_resolve_stream(const ResolveArgs& A, unsigned int* fix_list, 
 		if (alp) TAA_STREAM_GO(true, true, true, 0, 6);
 		TAA_STREAM_GO(true, false, true, 0, 6);
 	}
-	if (diag) { if (alp) TAA_STREAM_GO(false, true, true, 0, 8); TAA_STREAM_GO(false, false, true, 0, 8); }
-	if (alp) TAA_STREAM_GO(false, true, false, 0, 8);
-	if (minb_env == 6) TAA_STREAM_GO(false, false, false, 0, 6);
-	if (minb_env == 7) TAA_STREAM_GO(false, false, false, 0, 7);
-	TAA_STREAM_GO(false, false, false, 0, 8);
+	if (diag) { if (alp) TAA_STREAM_GO(false, true, true, 0, 6); TAA_STREAM_GO(false, false, true, 0, 6); }
+	if (alp) TAA_STREAM_GO(false, true, false, 0, 6);
+	if (minb_env == 8) TAA_STREAM_GO(false, false, false, 0, 8);
+	if (minb_env == 5) TAA_STREAM_GO(false, false, false, 0, 5);
+	TAA_STREAM_GO(false, false, false, 0, 6);
 #undef TAA_STREAM_GO
 }
 
