@@ -58,7 +58,7 @@ struct __align__(128) WarpSmem {
 	unsigned char craw[Cfg<REJ>::NR * ROWB];          // colour rows:   ring row (g - (Y0 - 2)) % NR holds image row g
 	unsigned char vraw[Cfg<REJ>::NR * ROWB];          // velocity rows: ring row (g - (Y0 - 3)) % NR holds image row g
 	unsigned char dt[REJ ? Cfg<REJ>::NR * DROWB : 128];  // depth rows, as colour
-	uint4 tabA[32];                                   // uniform motion: Catmull-Rom y weights of output row Y0 - 1 + t, permuted to the window's register order
+	uint4 tabA[32];                                   // uniform motion: Catmull-Rom y weights of output row Y0 - 1 + t
 	uint4 tabB[32];                                   // output row: velocity footprint rows (ring offsets lo | hi << 16), weight, v, history v
 	uint4 tabC[32];                                   // x, y: sampled colour row: ring offsets m | n << 16, bleed weight (half bits); y bit 31, z: output row: hv outside [0, 1), (int)(hv * H);
 	                                                  // w: uniform motion: byte offset of the history row requested while output row t - 2 is evaluated
@@ -488,13 +488,7 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		const float v = ((float)g + 0.5f) / fH;
 		const float hv = v - vxy.y;
 		const AxisW wy = catmull_axis_k(hv, fH, invh, (float)(K0 + 1 + i));
-		// the window keeps history row K0 + i + j in register slot (i + j) & 3: slot p carries weight (p - i) & 3
-		{
-			const int r = i & 3;  // rotate the four weights by r positions (selects: an indexed register array would live in local memory)
-			const float a0 = (r & 1) ? wy.w[3] : wy.w[0], a1 = (r & 1) ? wy.w[0] : wy.w[1], a2 = (r & 1) ? wy.w[1] : wy.w[2], a3 = (r & 1) ? wy.w[2] : wy.w[3];
-			const float b0 = (r & 2) ? a2 : a0, b1 = (r & 2) ? a3 : a1, b2 = (r & 2) ? a0 : a2, b3 = (r & 2) ? a1 : a3;
-			sm.tabA[lane] = make_uint4(__float_as_uint(b0), __float_as_uint(b1), __float_as_uint(b2), __float_as_uint(b3));
-		}
+		sm.tabA[lane] = make_uint4(__float_as_uint(wy.w[0]), __float_as_uint(wy.w[1]), __float_as_uint(wy.w[2]), __float_as_uint(wy.w[3]));
 		uint4 tb = sm.tabB[lane];
 		tb.w = __float_as_uint(hv);
 		sm.tabB[lane] = tb;
@@ -669,17 +663,19 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 			// sampled row y + 1 joins the rolling box
 			F3 S1a, S2a, S1b, S2b;
 			advance_box(std::integral_constant<int, PH & 1>{}, tcn, S1a, S2a, S1b, S2b);
-			// the footprints, filtered vertically
-			const float ar = fmaf(wy3, hA[3].r, fmaf(wy2, hA[2].r, fmaf(wy1, hA[1].r, wy0 * hA[0].r)));
-			const float ag = fmaf(wy3, hA[3].g, fmaf(wy2, hA[2].g, fmaf(wy1, hA[1].g, wy0 * hA[0].g)));
-			const float ab = fmaf(wy3, hA[3].b, fmaf(wy2, hA[2].b, fmaf(wy1, hA[1].b, wy0 * hA[0].b)));
-			const float br = fmaf(wy3, hB[3].r, fmaf(wy2, hB[2].r, fmaf(wy1, hB[1].r, wy0 * hB[0].r)));
-			const float bg = fmaf(wy3, hB[3].g, fmaf(wy2, hB[2].g, fmaf(wy1, hB[1].g, wy0 * hB[0].g)));
-			const float bb = fmaf(wy3, hB[3].b, fmaf(wy2, hB[2].b, fmaf(wy1, hB[1].b, wy0 * hB[0].b)));
+			// the footprints, filtered vertically: history row K0 + i + j sits in register slot (i + j) & 3 = (PH + j) & 3. Summed in the order of
+			// the rows, like the general rows do: the two paths give the same bits
+			constexpr int J0 = PH & 3, J1 = (PH + 1) & 3, J2 = (PH + 2) & 3, J3 = (PH + 3) & 3;
+			const float ar = fmaf(wy3, hA[J3].r, fmaf(wy2, hA[J2].r, fmaf(wy1, hA[J1].r, wy0 * hA[J0].r)));
+			const float ag = fmaf(wy3, hA[J3].g, fmaf(wy2, hA[J2].g, fmaf(wy1, hA[J1].g, wy0 * hA[J0].g)));
+			const float ab = fmaf(wy3, hA[J3].b, fmaf(wy2, hA[J2].b, fmaf(wy1, hA[J1].b, wy0 * hA[J0].b)));
+			const float br = fmaf(wy3, hB[J3].r, fmaf(wy2, hB[J2].r, fmaf(wy1, hB[J1].r, wy0 * hB[J0].r)));
+			const float bg = fmaf(wy3, hB[J3].g, fmaf(wy2, hB[J2].g, fmaf(wy1, hB[J1].g, wy0 * hB[J0].g)));
+			const float bb = fmaf(wy3, hB[J3].b, fmaf(wy2, hB[J2].b, fmaf(wy1, hB[J1].b, wy0 * hB[J0].b)));
 			float aa = 0.f, ba = 0.f;
 			if (REJ) {
-				aa = fmaf(wy3, hA[3].a, fmaf(wy2, hA[2].a, fmaf(wy1, hA[1].a, wy0 * hA[0].a)));
-				ba = fmaf(wy3, hB[3].a, fmaf(wy2, hB[2].a, fmaf(wy1, hB[1].a, wy0 * hB[0].a)));
+				aa = fmaf(wy3, hA[J3].a, fmaf(wy2, hA[J2].a, fmaf(wy1, hA[J1].a, wy0 * hA[J0].a)));
+				ba = fmaf(wy3, hB[J3].a, fmaf(wy2, hB[J2].a, fmaf(wy1, hB[J1].a, wy0 * hB[J0].a)));
 			}
 			// rejection (taa.comp:787-823), exact predicates
 			bool rejA = false, rejB = false;
@@ -724,20 +720,23 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 			hfilter_pair<REJ>(q0, q1, q2, q3, q4, wA, wB, hA[PH], hB[PH]);
 		};
 
+		// (The row counter advances through an opaque instruction that stays behind the rows' stores. With the plain `i += 2` the increment is
+		// hoisted to the top of the loop body, and in variants that spill ptxas 12.9 was seen to re-materialise `i + 3`, the table index of the
+		// third row, from the ALREADY incremented register: that row then read the table entries of four rows further down.)
 		while (i < nr) {
 			step_begin(i);
 			if (!uni) { begun = true; break; }
 			fast_row(std::integral_constant<int, 0>{}, i);
 			if (i + 1 < nr) fast_row(std::integral_constant<int, 1>{}, i + 1);
 			step_end(i);
-			i += 2;
+			asm volatile("add.s32 %0, %0, 2;" : "+r"(i));
 			if (i >= nr) break;
 			step_begin(i);
 			if (!uni) { begun = true; break; }
 			fast_row(std::integral_constant<int, 2>{}, i);
 			if (i + 1 < nr) fast_row(std::integral_constant<int, 3>{}, i + 1);
 			step_end(i);
-			i += 2;
+			asm volatile("add.s32 %0, %0, 2;" : "+r"(i));
 		}
 	}
 
@@ -949,6 +948,10 @@ bool stream_supports(const ResolveArgs& A) {
 	static const bool off = [] { const char* v = getenv("TAA_TUNED_VARIANT"); return v && (v[0] == 's' || v[0] == 't'); }();  // "strip" / "tile": A/B partners
 	if (off || !encode_fn()) return false;
 	const TaaParameters& P = A.ubo.param[0];
+	// The rejection variants (config 3) still run faster on the strip kernel (0.216 against 0.369 ms per 4K frame on B200): their uniform-motion
+	// rows carry too much predicate and addressing work here yet. TAA_STREAM_REJ=1 routes them through this kernel (tests, tuning).
+	static const bool rej_too = [] { const char* v = getenv("TAA_STREAM_REJ"); return v && v[0] == '1'; }();
+	if (!rej_too && (P.mDepthCulling || P.mRejectOutside || P.mDynamicAntiGhosting)) return false;
 	if (!tma_able(A.color) || !tma_able(A.velocity)) return false;
 	if (P.mDepthCulling && !tma_able(A.depth)) return false;
 	return true;
