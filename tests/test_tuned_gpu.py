@@ -356,6 +356,22 @@ def test_tile_kernel_variant_in_a_subprocess():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("env", [dict(TAA_TUNED_VARIANT="strip"), dict(TAA_STREAM_REJ="1")], ids=["strip", "stream-rej"])
+def test_other_kernels_of_the_family_in_a_subprocess(env):
+    """The default dispatch sends the plain variants to the streaming kernel and the rejection variants to the strip kernel. The other
+    pairing honours the same contract: the strip kernel on everything (TAA_TUNED_VARIANT=strip), the streaming kernel on the rejection
+    variants too (TAA_STREAM_REJ=1)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_tuned_gpu.py"), "-q", "-x", "-m", "gpu", "-k",
+                        "test_single_frame or test_each_switch_of_the_family or test_tiny_and_ragged_sizes or test_extreme_and_non_finite_motion or "
+                        "test_fixup_pass_is_bit_exact or test_row_bands_equal_whole_frame or test_uniform_motion_tiles or test_64_frame_sequence"],
+                       env=dict(os.environ, **env), capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("cfg,launches", [("config2", 1), ("config3", 2)])
 def test_without_a_mask_binding(oracle, cfg, launches):
     """`rectified` is reported through the mask alone: without a mask binding the fix-up pass runs only where a rejection predicate can be
