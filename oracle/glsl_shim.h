@@ -200,9 +200,31 @@ inline float abs(float a) { return std::fabs(a); }
 inline float floor(float a) { return std::floor(a); }
 inline float sqrt(float a) { return std::sqrt(a); }
 inline float fract(float a) { return a - std::floor(a); }
-inline float sin(float a) { return std::sin(a); }
-inline float cos(float a) { return std::cos(a); }
+inline float sin(float a);
+inline float cos(float a);
 inline float mix(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+
+// sin and cos as this repository pins them. GLSL leaves their precision to the implementation (and no Vulkan driver exists on either box), so the
+// oracle, the reference-shader shim (oracle/glsl_shim.h) and the CUDA kernels (taa_device.cuh) all evaluate THIS function text: Cody-Waite
+// reduction by pi/2 in three steps, the single-precision minimax polynomials of the Cephes library on [-pi/4, pi/4], one IEEE binary32 operation
+// per written operation (the three files are compiled without contraction). Arguments too large to reduce (>= 1e9) read as 0; non-finite ones give NaN.
+inline void taa_sincos(float x, float* s, float* c) {
+	if (!(std::fabs(x) < 1.0e9f)) { *s = x - x; *c = (x - x) + 1.0f; return; }
+	const float k = std::floor(x * 0.636619772f + 0.5f);
+	float r = x - k * 1.5703125f;
+	r = r - k * 4.837512969970703125e-4f;
+	r = r - k * 7.54978995489188216e-8f;
+	const float z = r * r;
+	const float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+	const float pc = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+	const int q = (int)k & 3;
+	*s = q == 0 ? ps : q == 1 ? pc : q == 2 ? -ps : -pc;
+	*c = q == 0 ? pc : q == 1 ? -ps : q == 2 ? -pc : ps;
+}
+inline float taa_sin(float x) { float s, c; taa_sincos(x, &s, &c); return s; }
+inline float taa_cos(float x) { float s, c; taa_sincos(x, &s, &c); return c; }
+inline float sin(float a) { return taa_sin(a); }
+inline float cos(float a) { return taa_cos(a); }
 
 // integer vectors
 inline ivec2 operator+(const ivec2& a, const ivec2& b) { return ivec2(a.x + b.x, a.y + b.y); }

@@ -53,6 +53,27 @@
 #include <omp.h>
 #endif
 
+// sin and cos as this repository pins them. GLSL leaves their precision to the implementation (and no Vulkan driver exists on either box), so the
+// oracle, the reference-shader shim (oracle/glsl_shim.h) and the CUDA kernels (taa_device.cuh) all evaluate THIS function text: Cody-Waite
+// reduction by pi/2 in three steps, the single-precision minimax polynomials of the Cephes library on [-pi/4, pi/4], one IEEE binary32 operation
+// per written operation (the three files are compiled without contraction). Arguments too large to reduce (>= 1e9) read as 0; non-finite ones give NaN.
+static inline void taa_sincos(float x, float* s, float* c) {
+	if (!(std::fabs(x) < 1.0e9f)) { *s = x - x; *c = (x - x) + 1.0f; return; }
+	const float k = std::floor(x * 0.636619772f + 0.5f);
+	float r = x - k * 1.5703125f;
+	r = r - k * 4.837512969970703125e-4f;
+	r = r - k * 7.54978995489188216e-8f;
+	const float z = r * r;
+	const float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+	const float pc = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+	const int q = (int)k & 3;
+	*s = q == 0 ? ps : q == 1 ? pc : q == 2 ? -ps : -pc;
+	*c = q == 0 ? pc : q == 1 ? -ps : q == 2 ? -pc : ps;
+}
+static inline float taa_sin(float x) { float s, c; taa_sincos(x, &s, &c); return s; }
+static inline float taa_cos(float x) { float s, c; taa_sincos(x, &s, &c); return c; }
+
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -563,7 +584,7 @@ struct Shader {
 	// taa.comp:551-556
 	vec4 noise(vec2 uv) const {
 		vec2 seed = uv + ubo->mSinTime[0] + 0.6959174f;
-		float s = sinf(dot(seed, vec2{12.9898f, 78.233f}));
+		float s = taa_sin(dot(seed, vec2{12.9898f, 78.233f}));
 		vec4 nRand = {gfract(s * 43758.5453f), gfract(s * 28001.8384f), gfract(s * 50849.4141f), gfract(s * 12996.89f)};
 		vec4 sRand = nRand * 2.0f - 1.0f;
 		return sRand * params.mNoiseFactor;
@@ -577,7 +598,7 @@ struct Shader {
 	// taa.comp:574-580
 	vec3 sample_normal(ivec2 iuv) const {
 		vec4 uvNormal = fetch_rgba32f(uCurrentUvNrm, iuv.x, iuv.y);
-		return {cosf(uvNormal.z) * cosf(uvNormal.w), sinf(uvNormal.z) * cosf(uvNormal.w), sinf(uvNormal.w)};
+		return {taa_cos(uvNormal.z) * taa_cos(uvNormal.w), taa_sin(uvNormal.z) * taa_cos(uvNormal.w), taa_sin(uvNormal.w)};
 	}
 	// taa.comp:582-587
 	static vec2 sobel(float c00, float c01, float c02, float c10, float c12, float c20, float c21, float c22) {
@@ -1199,6 +1220,11 @@ vec4 fxaa_pixel(const Tex& tex, vec2 pos, vec2 rcpFrame, float subpix, float edg
 }  // namespace
 
 extern "C" {
+
+// the pinned sin / cos, for the unit test that bounds their error against libm
+void taa_oracle_sincos(const float* x, float* s, float* c, int n) {
+	for (int i = 0; i < n; ++i) taa_sincos(x[i], &s[i], &c[i]);
+}
 
 // antialias_fxaa.comp:30-64: pixels whose seg-mask says 1 (FXAA) run FxaaPixelShader on the prepared image (luma in alpha), all
 // others are copied. gather4: see fxaa_pixel.

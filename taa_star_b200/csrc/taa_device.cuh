@@ -160,6 +160,26 @@ __device__ __forceinline__ float tex_r32f(const Img& im, int w, int h, float s, 
 	return lerpf(lerpf(t00, t10, cx.a), lerpf(t01, t11, cx.a), cy.a);
 }
 
+// sin and cos as this repository pins them. GLSL leaves their precision to the implementation (and no Vulkan driver exists on either box), so the
+// oracle, the reference-shader shim (oracle/glsl_shim.h) and the CUDA kernels (taa_device.cuh) all evaluate THIS function text: Cody-Waite
+// reduction by pi/2 in three steps, the single-precision minimax polynomials of the Cephes library on [-pi/4, pi/4], one IEEE binary32 operation
+// per written operation (the three files are compiled without contraction). Arguments too large to reduce (>= 1e9) read as 0; non-finite ones give NaN.
+__device__ __forceinline__ void taa_sincos(float x, float* s, float* c) {
+	if (!(fabsf(x) < 1.0e9f)) { *s = x - x; *c = (x - x) + 1.0f; return; }
+	const float k = floorf(x * 0.636619772f + 0.5f);
+	float r = x - k * 1.5703125f;
+	r = r - k * 4.837512969970703125e-4f;
+	r = r - k * 7.54978995489188216e-8f;
+	const float z = r * r;
+	const float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+	const float pc = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+	const int q = (int)k & 3;
+	*s = q == 0 ? ps : q == 1 ? pc : q == 2 ? -ps : -pc;
+	*c = q == 0 ? pc : q == 1 ? -ps : q == 2 ? -pc : ps;
+}
+__device__ __forceinline__ float taa_sin(float x) { float s, c; taa_sincos(x, &s, &c); return s; }
+__device__ __forceinline__ float taa_cos(float x) { float s, c; taa_sincos(x, &s, &c); return c; }
+
 // ---- colour space (taa.comp:158-197) ------------------------------------------------------------
 __device__ __forceinline__ f3 rgb_to_ycocg(f3 c) {
 	return mk3(.25f * c.x + .5f * c.y + .25f * c.z, .5f * c.x - .5f * c.z, -.25f * c.x + .5f * c.y - .25f * c.z);

@@ -122,7 +122,7 @@ struct Px {
 	__device__ float luma_at(int x, int y) const { return rgb_to_ycocg(xyz(fetch_rgba16f(A.color, A.in_w, A.in_h, x, y, st))).x; }
 	__device__ f3 normal_at(int x, int y) const {
 		float4 n = fetch_rgba32f(A.uvnrm, A.in_w, A.in_h, x, y, st);
-		return mk3(cosf(n.z) * cosf(n.w), sinf(n.z) * cosf(n.w), sinf(n.w));
+		return mk3(taa_cos(n.z) * taa_cos(n.w), taa_sin(n.z) * taa_cos(n.w), taa_sin(n.w));
 	}
 	__device__ static float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 	template <class F>
@@ -418,7 +418,7 @@ __device__ __forceinline__ void resolve_pixel_exact(const ResolveArgs& A, const 
 	if (P.mUseYCoCg) aa = ycocg_to_rgb(aa);
 	if (P.mAddNoise) {  // noise()                                                        taa.comp:551-556
 		float sx = u + A.ubo.mSinTime[0] + 0.6959174f, sy = v + A.ubo.mSinTime[0] + 0.6959174f;
-		float s = sinf(sx * 12.9898f + sy * 78.233f);
+		float s = taa_sin(sx * 12.9898f + sy * 78.233f);
 		float n0 = s * 43758.5453f, n1 = s * 28001.8384f, n2 = s * 50849.4141f;
 		n0 = n0 - floorf(n0); n1 = n1 - floorf(n1); n2 = n2 - floorf(n2);
 		aa.x = aa.x + (n0 * 2.0f - 1.0f) * P.mNoiseFactor;

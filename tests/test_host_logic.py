@@ -257,3 +257,26 @@ def test_reprojection_matrices_match_glm_bit_for_bit(taalib):
         assert taalib.taa_reprojection_matrices(m["proj_cur"], m["view_cur"], m["proj_prev"], m["view_prev"], inv, hist) == 0
         assert [_bits(v) for v in hist] == c["history_view_proj"], f"pose {i}: P_prev * V_prev"
         assert [_bits(v) for v in inv] == c["inverse_view_proj"], f"pose {i}: inverse(P_cur * V_cur)"
+
+
+def test_pinned_sincos_is_close_to_libm(oracle):
+    """GLSL leaves sin / cos to the implementation; oracle, shim and kernels share one software version (taa_sincos). It has to be a sane
+    sin / cos: within 2e-7 of libm on the range the spherical normals use, finite-argument results in [-1, 1], NaN for non-finite arguments."""
+    import ctypes as C
+    import numpy as np
+    L = oracle.lib()
+    L.taa_oracle_sincos.restype = None
+    L.taa_oracle_sincos.argtypes = [C.POINTER(C.c_float)] * 3 + [C.c_int]
+    x = np.concatenate([np.linspace(-7.0, 7.0, 200001), np.linspace(-1000.0, 1000.0, 20001), [0.0, np.pi / 2, np.pi, 1.5 * np.pi, 2 * np.pi]]).astype(np.float32)
+    s, c = np.empty_like(x), np.empty_like(x)
+    ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    L.taa_oracle_sincos(ptr(x), ptr(s), ptr(c), x.size)
+    small = np.abs(x) <= 7.0
+    assert np.abs(s[small] - np.sin(x[small].astype(np.float64))).max() < 2e-7
+    assert np.abs(c[small] - np.cos(x[small].astype(np.float64))).max() < 2e-7
+    assert np.abs(s - np.sin(x.astype(np.float64))).max() < 1e-4 and np.abs(c - np.cos(x.astype(np.float64))).max() < 1e-4
+    assert np.abs(s).max() <= 1.0 + 1e-6 and np.abs(c).max() <= 1.0 + 1e-6
+    bad = np.array([np.inf, -np.inf, np.nan, 3e9], np.float32)
+    sb, cb = np.empty_like(bad), np.empty_like(bad)
+    L.taa_oracle_sincos(ptr(bad), ptr(sb), ptr(cb), bad.size)
+    assert np.isnan(sb[:3]).all() and np.isnan(cb[:3]).all() and sb[3] == 0.0 and cb[3] == 1.0

@@ -201,14 +201,18 @@ def test_segmentation_mask(oracle):
         u = configs.uniforms_for(p, f1.jitter_ndc)
         check_exact(oracle, u, ins, hist, hist_depth=f0.depth.numpy(), prev_matid=f0.matid.numpy(), prev_segmask=prev_seg,
                     want=("history_out", "result", "mask", "segmask"))
-    # the normal indicator goes through sin/cos (libm vs CUDA): allow a handful of threshold flips
+    # The normal indicator goes through sin/cos, which GLSL leaves to the implementation: oracle, reference-shader shim and CUDA kernel share one
+    # software sincos (taa_sincos), so the integer mask is bit-exact with the normal indicator too — alone, in the reference's default flag
+    # set (taa.hpp:61: all indicators) and with a heavy weight that puts many pixels near the threshold.
+    for flags, wnrm in ((abi.TAA_RTFLAG_NRM, 40.0), (abi.TAA_RTFLAG_NRM, 1.0), (all_flags, 1.0), (all_flags, 40.0), (0xffffffff & ~abi.TAA_RTFLAG_FXD, 4.0)):
+        p = with_params(configs.config3_full_chain(), mRayTraceAugment=1, mRayTraceAugmentFlags=flags, mRayTraceAugment_WNrm=wnrm, mRayTraceHistoryCount=8)
+        u = configs.uniforms_for(p, f1.jitter_ndc)
+        check_exact(oracle, u, ins, hist, hist_depth=f0.depth.numpy(), prev_matid=f0.matid.numpy(), prev_segmask=prev_seg,
+                    want=("history_out", "result", "mask", "segmask"))
     p = with_params(configs.config3_full_chain(), mRayTraceAugment=1, mRayTraceAugmentFlags=abi.TAA_RTFLAG_NRM, mRayTraceAugment_WNrm=40.0)
     u = configs.uniforms_for(p, f1.jitter_ndc)
     ref = oracle.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist, history_depth=f0.depth.numpy(), matid=ins["matid"],
                          uvnrm=ins["uvnrm"], want=("segmask",))
-    ctx = host.TaaContext((W, H), flags=abi.TAA_FLAG_EXACT)
-    got = run_gpu_resolve(ctx, u, ins, hist, hist_depth=f0.depth.numpy(), want=("segmask", "history_out"))
-    assert (ref["segmask"] != got["segmask"]).mean() < 1e-3
     assert 0.01 < (ref["segmask"] != 0).mean() < 0.99
 
 
