@@ -107,6 +107,11 @@ int build_resolve_args(taa_ctx* c, const taa_resolve_images* im, const TaaUnifor
 
 int run_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s) {
 	int launched = 0;
+	int cur = -1;  // a process may hold contexts on several devices: launch on the context's
+	if (cudaGetDevice(&cur) == cudaSuccess && cur != c->desc.device) {
+		cudaError_t e = cudaSetDevice(c->desc.device);
+		if (e != cudaSuccess) return cuda_fail(c, e, "cudaSetDevice");
+	}
 	cudaError_t e = dispatch_resolve(c, A, s, &launched);
 	c->launches += launched;
 	if (e != cudaSuccess) return cuda_fail(c, e, "taa resolve launch");
@@ -259,7 +264,8 @@ int taa_sharpen_cas(taa_ctx* c, const taa_image* src, const taa_image* dst, cons
 int taa_post_process(taa_ctx* c, const taa_image* src, const taa_image* debug, const taa_image* dst, const TaaPostProcessPush* pc, void* stream) {
 	PostImg io;
 	if (!pc) return TAA_E_INVALID_ARG;
-	if ((pc->debugL_show || pc->debugR_show) && !(debug && debug->data)) { set_error(c, "post_process: debug image required when debug*_show is set"); return TAA_E_INVALID_ARG; }
+	// (post_process.comp:69-75 never looks at the right-hand settings without a splitter: splitX < 0)
+	if ((pc->debugL_show || (pc->splitX >= 0 && pc->debugR_show)) && !(debug && debug->data)) { set_error(c, "post_process: debug image required when debug*_show is set"); return TAA_E_INVALID_ARG; }
 	int r = make_post(c, src, debug, dst, io);
 	if (r != TAA_OK) return r;
 	cudaError_t e = launch_post_process(io, *pc, (cudaStream_t)stream);
@@ -309,7 +315,7 @@ int taa_frame(taa_ctx* c, const taa_resolve_images* images, const TaaUniforms* u
 	const bool fxaa = chain->fxaa != 0, sharpen = chain->sharpener != 0, post = chain->postprocess != 0;
 	if (chain->sharpener < 0 || chain->sharpener > 2) { set_error(c, "mSharpener must be 0, 1 or 2 (taa.hpp:1418)"); return TAA_E_INVALID_ARG; }
 	if (fxaa && !images->segmask.data) { set_error(c, "taa_frame: FXAA needs the segmentation mask image (mRayTraceAugment)"); return TAA_E_INVALID_ARG; }
-	if (post && (chain->pp.debugL_show || chain->pp.debugR_show) && !images->debug.data) { set_error(c, "post_process: debug image required when debug*_show is set"); return TAA_E_INVALID_ARG; }
+	if (post && (chain->pp.debugL_show || (chain->pp.splitX >= 0 && chain->pp.debugR_show)) && !images->debug.data) { set_error(c, "post_process: debug image required when debug*_show is set"); return TAA_E_INVALID_ARG; }
 	taa_resolve_images im = *images;
 	const int64_t pitch = (int64_t)d.out_width * 8;
 	int stages = (fxaa ? 1 : 0) + ((sharpen || post) ? 1 : 0);  // launches after the resolve

@@ -72,6 +72,20 @@ int inv_cuda(taa_invokee* t, cudaError_t e, const char* what) {
 	return TAA_E_CUDA;
 }
 
+// the host-frame pipeline (streams, events, device copies of the G-buffers) is sized for one input size: torn down with the images
+void free_pipe(taa_invokee* t) {
+	if (!t->pipe_ready) return;
+	cudaStreamSynchronize(t->sUp); cudaStreamSynchronize(t->sCompute); cudaStreamSynchronize(t->sDown);
+	for (auto e : t->evUploaded) cudaEventDestroy(e);
+	for (auto e : t->evComputed) cudaEventDestroy(e);
+	for (auto e : t->evDone) cudaEventDestroy(e);
+	t->evUploaded.clear(); t->evComputed.clear(); t->evDone.clear();
+	cudaStreamDestroy(t->sUp); cudaStreamDestroy(t->sCompute); cudaStreamDestroy(t->sDown);
+	t->sUp = t->sCompute = t->sDown = nullptr;
+	t->slotBusy.clear();
+	t->pipe_ready = false;
+}
+
 void free_images(taa_invokee* t) {
 	for (auto& v : t->img) {
 		for (void* p : v) if (p) cudaFree(p);
@@ -136,13 +150,7 @@ int taa_invokee_create(taa_invokee** out, int32_t concurrent_frames, int32_t dev
 void taa_invokee_destroy(taa_invokee* t) {
 	if (!t) return;
 	cudaSetDevice(t->device);
-	if (t->pipe_ready) {
-		cudaStreamSynchronize(t->sUp); cudaStreamSynchronize(t->sCompute); cudaStreamSynchronize(t->sDown);
-		for (auto e : t->evUploaded) cudaEventDestroy(e);
-		for (auto e : t->evComputed) cudaEventDestroy(e);
-		for (auto e : t->evDone) cudaEventDestroy(e);
-		cudaStreamDestroy(t->sUp); cudaStreamDestroy(t->sCompute); cudaStreamDestroy(t->sDown);
-	}
+	free_pipe(t);
 	for (auto e : t->evStart) cudaEventDestroy(e);
 	for (auto e : t->evStop) cudaEventDestroy(e);
 	free_images(t);
@@ -157,6 +165,7 @@ int taa_invokee_set_source_image_views(taa_invokee* t, int32_t target_w, int32_t
 	if (!t || target_w <= 0 || target_h <= 0 || in_w <= 0 || in_h <= 0) return TAA_E_INVALID_ARG;
 	cudaError_t e = cudaSetDevice(t->device);
 	if (e != cudaSuccess) return inv_cuda(t, e, "cudaSetDevice");
+	free_pipe(t);  // (a host-frame pipeline of the old size: frames in flight are waited for, ensure_pipe() rebuilds it)
 	free_images(t);
 	if (t->ctx) { taa_destroy(t->ctx); t->ctx = nullptr; }
 	taa_desc d{};
@@ -352,9 +361,18 @@ static int render_with_sources(taa_invokee* t, int64_t frame, const std::vector<
 		if (r != TAA_OK) { inv_error(t, "taa_frame: %s", taa_last_error_string(t->ctx)); return r; }
 		final_img = fin;
 	} else {
-		// "blit" colour -> result (taa.hpp:1176); only defined here for equal formats and sizes
-		if (t->mUpsampling) { inv_error(t, "pass-through blit with upsampling is not supported"); return TAA_E_UNSUPPORTED; }
-		cudaError_t e = cudaMemcpyAsync(t->img[TAA_IMG_RESULT][i], cur.color, (size_t)W * H * 8, cudaMemcpyDeviceToDevice, stream);
+		// "blit" colour -> result (taa.hpp:1176): a plain copy for equal sizes, the nearest-texel scaling of vkCmdBlitImage with upsampling
+		cudaError_t e;
+		if (t->mUpsampling) {
+			taa::PostImg io{};
+			io.src = taa::Img{(const unsigned char*)cur.color, (long long)t->in_w * 8, 0, t->in_h};
+			io.dst = taa::ImgW{(unsigned char*)t->img[TAA_IMG_RESULT][i], (long long)W * 8, 0, H};
+			io.w = W; io.h = H;
+			e = taa::launch_blit_nearest(io, t->in_w, t->in_h, stream);
+			if (e == cudaSuccess) t->ctx->launches++;
+		} else {
+			e = cudaMemcpyAsync(t->img[TAA_IMG_RESULT][i], cur.color, (size_t)W * H * 8, cudaMemcpyDeviceToDevice, stream);
+		}
 		if (e != cudaSuccess) return inv_cuda(t, e, "blit colour -> result");
 		final_img = t->img[TAA_IMG_RESULT][i];
 	}
@@ -406,17 +424,24 @@ static int ensure_pipe(taa_invokee* t, bool uvnrm, bool matid) {
 		cudaEventCreateWithFlags(&t->evDone[i], cudaEventDisableTiming);
 	}
 	t->dsrc.assign(t->CF, taa_source_views{});
+	t->owns_dsrc = true;   // (set first: a failure below leaves a partly allocated set that free_images() / free_pipe() release)
+	t->pipe_ready = true;
 	const size_t px = (size_t)t->in_w * t->in_h;
 	for (int i = 0; i < t->CF; ++i) {
 		void *c = nullptr, *d = nullptr, *v = nullptr, *n = nullptr, *m = nullptr;
-		if ((e = cudaMalloc(&c, px * 8)) != cudaSuccess || (e = cudaMalloc(&d, px * 4)) != cudaSuccess || (e = cudaMalloc(&v, px * 8)) != cudaSuccess)
-			return inv_cuda(t, e, "cudaMalloc(device G-buffer)");
-		if (uvnrm && (e = cudaMalloc(&n, px * 16)) != cudaSuccess) return inv_cuda(t, e, "cudaMalloc(uvnrm)");
-		if (matid && (e = cudaMalloc(&m, px * 4)) != cudaSuccess) return inv_cuda(t, e, "cudaMalloc(matid)");
+		if ((e = cudaMalloc(&c, px * 8)) == cudaSuccess && (e = cudaMalloc(&d, px * 4)) == cudaSuccess) e = cudaMalloc(&v, px * 8);
+		if (e == cudaSuccess && uvnrm) e = cudaMalloc(&n, px * 16);
+		if (e == cudaSuccess && matid) e = cudaMalloc(&m, px * 4);
 		t->dsrc[i] = taa_source_views{c, d, n, v, m, nullptr};
+		if (e != cudaSuccess) {
+			int r = inv_cuda(t, e, "cudaMalloc(device G-buffer)");
+			free_pipe(t);
+			for (auto& sv : t->dsrc) { cudaFree((void*)sv.color); cudaFree((void*)sv.depth); cudaFree((void*)sv.velocity); cudaFree((void*)sv.uvnrm); cudaFree((void*)sv.matid); }
+			t->dsrc.clear();
+			t->owns_dsrc = false;
+			return r;
+		}
 	}
-	t->owns_dsrc = true;
-	t->pipe_ready = true;
 	return TAA_OK;
 }
 

@@ -29,6 +29,8 @@ cudaError_t launch_resolve_stream(const ResolveArgs& args, unsigned int* fix_lis
 
 // follow-on passes, one kernel each as the reference dispatches them (taa_post.cu)
 struct PostImg { Img src; Img debug; ImgW dst; int w, h; };
+// avk::blit_image (nearest, whole image -> whole image): io.src is src_w x src_h, io.dst is io.w x io.h
+cudaError_t launch_blit_nearest(const PostImg& io, int src_w, int src_h, cudaStream_t stream);
 cudaError_t launch_sharpen(const PostImg& io, float sharpeningFactor, cudaStream_t stream);           // sharpen.comp
 cudaError_t launch_cas(const PostImg& io, const TaaCasPush& pc, cudaStream_t stream);                 // sharpen_cas.comp
 cudaError_t launch_post_process(const PostImg& io, const TaaPostProcessPush& pc, cudaStream_t stream); // post_process.comp

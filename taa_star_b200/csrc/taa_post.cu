@@ -108,10 +108,25 @@ __global__ void __launch_bounds__(256) post_process_kernel(const __grid_constant
 	st_rgba16f(io.dst, x, y, val);
 }
 
+// vkCmdBlitImage with VK_FILTER_NEAREST over the whole images (avk::blit_image, gears_vk/auto_vk/src/avk.cpp:7803-7829, as taa.hpp:1176 calls it when
+// anti-aliasing is off or on the very first frame): destination texel (x, y) takes source texel floor((x + 0.5) * sw / dw), floor((y + 0.5) * sh / dh)
+__global__ void __launch_bounds__(256) blit_nearest_kernel(const __grid_constant__ PostImg io, const int sw, const int sh) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= io.w || y >= io.h) return;
+	const int sx = min((int)floorf(((float)x + 0.5f) * ((float)sw / (float)io.w)), sw - 1);
+	const int sy = min((int)floorf(((float)y + 0.5f) * ((float)sh / (float)io.h)), sh - 1);
+	st_rgba16f(io.dst, x, y, ld_rgba16f(io.src, sx, sy, nullptr));
+}
+
 inline dim3 grid2d(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
 
 }  // namespace
 
+cudaError_t launch_blit_nearest(const PostImg& io, int src_w, int src_h, cudaStream_t stream) {
+	dim3 b(32, 8);
+	blit_nearest_kernel<<<grid2d(io.w, io.h, b), b, 0, stream>>>(io, src_w, src_h);
+	return cudaGetLastError();
+}
 cudaError_t launch_sharpen(const PostImg& io, float factor, cudaStream_t stream) {
 	dim3 b(32, 8);
 	sharpen_kernel<<<grid2d(io.w, io.h, b), b, 0, stream>>>(io, factor);

@@ -771,11 +771,14 @@ template <bool REJ, bool ALPHA, bool DIAG, int MINB, int UNR>
 cudaError_t launch_variant(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, float band, cudaStream_t stream) {
 	using StripSmem = StripSmemT<REJ>;
 	auto kern = taa_resolve_strip_kernel<REJ, ALPHA, DIAG, MINB, UNR>;
-	static bool configured = false;  // per variant
-	if (!configured) {
+	static bool configured[64] = {false};  // per variant and per device: the attribute belongs to the (function, device) pair
+	int dev = 0;
+	cudaGetDevice(&dev);
+	dev &= 63;
+	if (!configured[dev]) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StripSmem));
 		if (e != cudaSuccess) return e;
-		configured = true;
+		configured[dev] = true;
 	}
 	dim3 grid((A.out_w + TW - 1) / TW, (A.band_rows + TH - 1) / TH);
 	static const bool use_bulk = [] { const char* v = getenv("TAA_STRIP_BULK"); return v && v[0] == '1'; }();

@@ -206,3 +206,92 @@ def test_invokee_render_sequence(oracle, sharpener):
 
 def test_invokee_host_buffer_frames(oracle):
     _run_invokee_sequence(oracle, host_frames=True, sharpener=2)
+
+
+def test_invokee_with_upsampling(oracle):
+    """TAAU through the invokee (in_size != out_size, taa.hpp:292): the very first frame is avk::blit_image's nearest-texel scaling of the
+    colour buffer (taa.hpp:1176, avk.cpp:7829), the following frames are resolved at the target resolution."""
+    CF = 3
+    iw, ih, ow, oh = 96, 54, 192, 108
+    sc = SyntheticScene(iw, ih, pan_px=(0.75, 0.5))
+    frames = [sc.frame(n) for n in range(4)]
+    t = host.Taa(CF, flags=abi.TAA_FLAG_EXACT)
+    p = configs.config2_resolve()
+    for i in range(2):
+        C.memmove(C.addressof(t.mParameters[i]), C.addressof(p), C.sizeof(p))
+    t.settings.jitter.mSampleDistribution = 2
+    t.settings.mPostProcessEnabled = 0
+    slots = [dict(color=torch.empty_like(frames[0].color).cuda(), depth=torch.empty_like(frames[0].depth).cuda(),
+                  velocity=torch.empty_like(frames[0].velocity).cuda()) for _ in range(CF)]
+    t.set_source_image_views((ow, oh), [x["color"] for x in slots], [x["depth"] for x in slots], None, [x["velocity"] for x in slots])
+    hist = [np.zeros((oh, ow, 4), np.float16) for _ in range(CF)]
+    for n, f in enumerate(frames):
+        i, last = n % CF, (n + CF - 1) % CF
+        for k in slots[i]:
+            slots[i][k].copy_(getattr(f, k))
+        t.get_jittered_projection_matrix(f.proj, n)
+        t.save_history_proj_matrix(f.proj, n)
+        t.update(n, f.view)
+        ptr = t.render(n)
+        torch.cuda.synchronize()
+        got = t.image_by_ptr(ptr).cpu().numpy()
+        assert got.shape == (oh, ow, 4)
+        if n == 0:
+            ys = np.minimum(np.floor((np.arange(oh, dtype=np.float32) + np.float32(0.5)) * (np.float32(ih) / np.float32(oh))).astype(int), ih - 1)
+            xs = np.minimum(np.floor((np.arange(ow, dtype=np.float32) + np.float32(0.5)) * (np.float32(iw) / np.float32(ow))).astype(int), iw - 1)
+            want = f.color.numpy()[ys][:, xs]
+        else:
+            (jx, jy), _ = host.jitter_offset_for_frame(n, ow, oh, sample_distribution=2)
+            u = configs.uniforms_for(p, (jx, jy), upsampling=True)
+            u.mSinTime[0] = u.mSinTime[1] = u.mSinTime[2] = u.mSinTime[3] = 0.0
+            m = lambda a: (C.c_float * 16)(*a)
+            abi.load_library().taa_reprojection_matrices(m(f.proj), m(f.view), m(frames[n - 1].proj), m(frames[n - 1].view),
+                                                         u.mInverseViewProjMatrix, u.mHistoryViewProjMatrix)
+            ins = np_inputs(f)
+            ref = oracle.resolve(u, ins["color"], ins["depth"], ins["velocity"], hist[last], history_depth=frames[n - 1].depth.numpy(),
+                                 out_size=(ow, oh), want=("history_out", "result"))
+            want = ref["result"]
+            hist[i] = ref["history_out"]
+        r = mismatch_report(f"upsampling frame {n}", want, got)
+        assert r is None, r
+    t.close()
+
+
+def test_invokee_new_size_after_host_frames():
+    """set_source_image_views() after frame_host() has run (a resolution change): the host-frame pipeline is rebuilt for the new size."""
+    t = host.Taa(3)
+    p = configs.config2_resolve()
+    for i in range(2):
+        C.memmove(C.addressof(t.mParameters[i]), C.addressof(p), C.sizeof(p))
+    t.settings.jitter.mSampleDistribution = 2
+    for (w, h) in ((160, 90), (224, 126), (96, 54)):
+        sc = SyntheticScene(w, h)
+        t.set_sizes_for_host_frames((w, h), (w, h))
+        outs = []
+        for n in range(4):
+            f = sc.frame(n)
+            fin = torch.empty(h, w, 4, dtype=torch.float16).pin_memory()
+            hc, hd, hv = f.color.pin_memory(), f.depth.pin_memory(), f.velocity.pin_memory()
+            t.frame_host(n, hc, hd, hv, f.view, f.proj, fin)
+            t.wait(n)
+            outs.append(fin.numpy().copy())
+        assert np.isfinite(outs[-1].astype(np.float32)).all() and 0.05 < float(outs[-1][..., :3].astype(np.float32).mean()) < 0.95
+    t.close()
+
+
+def test_right_hand_debug_setting_without_a_splitter(oracle):
+    """param[1].mDebugToScreenOutput is copied into the post-process constants unconditionally (taa.hpp:955-959), but post_process.comp never
+    looks at the right-hand settings without a splitter: the frame renders normally, no debug image needed."""
+    sc = SyntheticScene(W, H)
+    f0, f1 = sc.frame(1), sc.frame(2)
+    ins, hist = np_inputs(f1), f0.color.numpy().copy()
+    u = configs.uniforms_for(configs.config2_resolve(), f1.jitter_ndc)
+    pp = host.postprocess_default(W, H)
+    pp.debugR_show = 1
+    ch = chain_of(0, 1, pp)
+    ref, ref_final = oracle_chain(oracle, u, ins, hist, None, ch)
+    ctx = host.TaaContext((W, H), flags=abi.TAA_FLAG_EXACT)
+    final, ho = gpu_out(), gpu_out()
+    ctx.frame(u, ch, final, color=to_dev(ins["color"]), depth=to_dev(ins["depth"]), velocity=to_dev(ins["velocity"]), history_in=to_dev(hist), history_out=ho)
+    torch.cuda.synchronize()
+    assert mismatch_report("final", ref_final, final.cpu().numpy()) is None
