@@ -241,7 +241,7 @@ def test_invokee_with_upsampling(oracle):
             xs = np.minimum(np.floor((np.arange(ow, dtype=np.float32) + np.float32(0.5)) * (np.float32(iw) / np.float32(ow))).astype(int), iw - 1)
             want = f.color.numpy()[ys][:, xs]
         else:
-            (jx, jy), _ = host.jitter_offset_for_frame(n, ow, oh, sample_distribution=2)
+            (jx, jy), _ = host.jitter_offset_for_frame(n, iw, ih, sample_distribution=2)  # the input resolution (taa.hpp:153-154)
             u = configs.uniforms_for(p, (jx, jy), upsampling=True)
             u.mSinTime[0] = u.mSinTime[1] = u.mSinTime[2] = u.mSinTime[3] = 0.0
             m = lambda a: (C.c_float * 16)(*a)
