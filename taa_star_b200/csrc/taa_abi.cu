@@ -102,6 +102,9 @@ int build_resolve_args(taa_ctx* c, const taa_resolve_images* im, const TaaUnifor
 	A.band_rows = d.band_rows;
 	A.status = c->d_status;
 	A.ubo = *u;
+	A.final_img = ImgW{nullptr, 0, 0, 0};
+	A.epilogue = 0;
+	A.epilogue_k = 0.f;
 	return TAA_OK;
 }
 
@@ -328,11 +331,40 @@ int taa_frame(taa_ctx* c, const taa_resolve_images* images, const TaaUniforms* u
 		return TAA_OK;
 	};
 	// stage 0: resolve. Its screen result goes to the caller's image, or to `final` when nothing follows, or to scratch.
-	if (!im.result.data) {
-		if (stages == 0) im.result = *final_img;
-		else { int r = scratch(im.result); if (r != TAA_OK) return r; }
+	const bool result_given = im.result.data != nullptr;
+	auto prepare_result = [&]() -> int {
+		if (result_given) return TAA_OK;
+		if (stages == 0) { im.result = *final_img; return TAA_OK; }
+		return scratch(im.result);
+	};
+	// ---- the fused chain: [sharpen | CAS] (+ an identity post-process) in the resolve's epilogue, one launch and no intermediate image ----
+	// Admissible when post_process.comp would only copy (no zoom box, no splitter, no debug view), FXAA is off and the call takes a plain
+	// variant of the streaming kernel with nothing left to the exact pass (stream_epilogue_ok). Without a sharpener an identity post-process
+	// is a copy: the resolve then writes its screen result straight into `final`.
+	const bool pp_identity = !post || (!chain->pp.zoom && chain->pp.splitX < 0 && !chain->pp.debugL_show);
+	if (!fxaa && pp_identity && (sharpen || post) && check_pitch(c, *final_img, d.out_width, 8, "final") == TAA_OK && !(c->desc.flags & TAA_FLAG_EXACT)) {
+		taa_resolve_images fim = *images;
+		if (!sharpen) {
+			if (!fim.result.data) {  // (a caller that wants both images still gets the copy below)
+				fim.result = *final_img;
+				return taa_resolve_ex(c, &fim, u, stream);
+			}
+		} else {
+			ResolveArgs A;
+			int r = build_resolve_args(c, &fim, u, A);
+			if (r != TAA_OK) return r;
+			if (stream_epilogue_ok(A, (c->desc.flags & TAA_FLAG_FIXUP_ALL) != 0) && final_img->data != fim.result.data && final_img->data != fim.history_out.data) {
+				fill_imgw(A.final_img, *final_img, d.out_height);
+				A.epilogue = chain->sharpener;
+				if (chain->sharpener == 1) A.epilogue_k = chain->sharpen.sharpeningFactor;
+				else memcpy(&A.epilogue_k, &chain->cas.const1[0], 4);
+				return run_resolve(c, A, (cudaStream_t)stream);
+			}
+		}
 	}
-	int r = taa_resolve_ex(c, &im, u, stream);
+	int r = prepare_result();
+	if (r != TAA_OK) return r;
+	r = taa_resolve_ex(c, &im, u, stream);
 	if (r != TAA_OK) return r;
 	taa_image last = im.result;
 	if (fxaa) {

@@ -33,6 +33,10 @@ struct ResolveArgs {
 	int band_y0, band_rows;
 	unsigned int* status;  // device word: bit0 = a read left the rows held by a band buffer
 	TaaUniforms ubo;
+	// the follow-on pass fused into the resolve (streaming kernel only; set by taa_frame when the chain allows it):
+	ImgW final_img;        // what sharpen.comp | sharpen_cas.comp (+ an identity post_process.comp) would have written
+	int epilogue;          // 0: none, 1: sharpen.comp, 2: sharpen_cas.comp
+	float epilogue_k;      // sharpening factor | CAS peak (const1.x)
 };
 
 // ---- scalar helpers -----------------------------------------------------------------------------

@@ -24,6 +24,8 @@ cudaError_t launch_resolve_strip(const ResolveArgs& args, unsigned int* fix_list
 // neighbourhood sums and a sliding history window; raw rows arrive through a per-warp ring of 2-D TMA boxes. stream_supports(): the
 // images can be described by tensor maps (16-byte aligned base and pitch) and the driver exports cuTensorMapEncodeTiled.
 bool stream_supports(const ResolveArgs& args);
+// args.epilogue != 0 (the sharpening pass evaluated in the resolve's epilogue, written to args.final_img) is admissible for this call
+bool stream_epilogue_ok(const ResolveArgs& args, bool fixup_all);
 cudaError_t launch_resolve_stream(const ResolveArgs& args, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next,
                                   bool fixup_all, int num_sms, cudaStream_t stream);
 

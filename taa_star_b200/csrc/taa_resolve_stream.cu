@@ -36,7 +36,7 @@ namespace {
 
 using namespace tuned;
 
-constexpr int OWS = 62;                     // output columns per warp strip
+constexpr int OWS = 62;                     // output columns per warp strip (60 with a fused sharpening epilogue: it needs resolved neighbours)
 constexpr int RWT = 72;                     // ring row: image columns Xb .. Xb + 71, Xb = 62 s - 4 (one TMA box row, 576 bytes)
 constexpr unsigned int ROWB = RWT * 8u;
 constexpr int SROWS = 2;                    // rows per slot = per TMA box
@@ -315,7 +315,35 @@ __device__ __forceinline__ void gather_history(const ResolveArgs& A, const float
 	hsa = REJ ? fmaf(ay.w[3], r3.a, fmaf(ay.w[2], r2.a, fmaf(ay.w[1], r1.a, ay.w[0] * r0.a))) : 0.f;
 }
 
-template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB>
+// ---- the sharpening pass fused into the resolve (EPI = 1: sharpen.comp:23-38, EPI = 2: sharpen_cas.comp + CasFilter, ffx_cas.h:408-537) --------
+// The reference writes the resolved image, reads it back through a five-texel plus and writes the sharpened image (taa.hpp:1111-1139): 16 bytes
+// of DRAM traffic per pixel that a resolve which still has the neighbours in registers does not need. Values are taken as the rgba16f image
+// would have returned them (rounded to fp16), the arithmetic is the one of taa_post.cu (this file is compiled without contraction).
+__device__ __forceinline__ float e_lo_sqrt(float a) { return __uint_as_float((__float_as_uint(a) >> 1) + 0x1fbc4639u); }  // ffx_a.h:1455-1457
+__device__ __forceinline__ float e_lo_rcp(float a) { return __uint_as_float(0x7ef07ebbu - __float_as_uint(a)); }
+__device__ __forceinline__ float e_med_rcp(float a) { float b = __uint_as_float(0x7ef19fffu - __float_as_uint(a)); return b * (-b * a + 2.0f); }
+template <int EPI>
+__device__ __forceinline__ F3 sharpen_px(const F3 up, const F3 lf, const F3 ce, const F3 rt, const F3 dn, const float k) {
+	F3 o;
+	if (EPI == 1) {  // C + (4C - L - R - T - B) * f, clamped to [0, 1]
+		o.x = clampf(ce.x + ((((4.0f * ce.x - lf.x) - rt.x) - up.x) - dn.x) * k, 0.f, 1.f);
+		o.y = clampf(ce.y + ((((4.0f * ce.y - lf.y) - rt.y) - up.y) - dn.y) * k, 0.f, 1.f);
+		o.z = clampf(ce.z + ((((4.0f * ce.z - lf.z) - rt.z) - up.z) - dn.z) * k, 0.f, 1.f);
+	} else {  // b = up, d = left, e = centre, f = right, h = down; only the green weight survives (ffx_cas.h:514-522)
+		const float mn = fminf(fminf(lf.y, fminf(ce.y, rt.y)), fminf(up.y, dn.y));
+		const float mx = fmaxf(fmaxf(lf.y, fmaxf(ce.y, rt.y)), fmaxf(up.y, dn.y));
+		float amp = clampf(fminf(mn, 1.0f - mx) * e_lo_rcp(mx), 0.f, 1.f);
+		amp = e_lo_sqrt(amp);
+		const float w = amp * k;
+		const float rw = e_med_rcp(1.0f + 4.0f * w);
+		o.x = clampf((up.x * w + lf.x * w + rt.x * w + dn.x * w + ce.x) * rw, 0.f, 1.f);
+		o.y = clampf((up.y * w + lf.y * w + rt.y * w + dn.y * w + ce.y) * rw, 0.f, 1.f);
+		o.z = clampf((up.z * w + lf.z * w + rt.z * w + dn.z * w + ce.z) * rw, 0.f, 1.f);
+	}
+	return o;
+}
+
+template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB, int EPI>
 __global__ void __launch_bounds__(32 * NWARP, MINB)
 taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmV,
                           const __grid_constant__ CUtensorMap tmD, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
@@ -331,13 +359,18 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	const float fW = (float)W, fH = (float)H;
 	const float invw = 1.0f / fW, invh = 1.0f / fH;
 	const int strip = blockIdx.x * NWARP + warp;
-	const int Y0 = A.band_y0 + blockIdx.y * R;
-	const int nr = min(R, A.band_y0 + A.band_rows - Y0);
-	const int Xs = strip * OWS - 2, Xb = Xs - 2;  // first sampled column, first ring column
+	// rows this unit owns (writes); with a sharpening epilogue it also resolves the row above and the row below them, whose values the
+	// plus-shaped stencil needs (whole frames only: the follow-on passes do not run on bands)
+	const int Yo = A.band_y0 + blockIdx.y * R;
+	const int no = min(R, A.band_y0 + A.band_rows - Yo);
+	const int Y0 = EPI ? max(Yo - 1, 0) : Yo;
+	const int nr = EPI ? min(Yo + no, H - 1) - Y0 + 1 : no;
+	constexpr int STEP_X = EPI ? OWS - 2 : OWS;
+	const int Xs = strip * STEP_X - 2, Xb = Xs - 2;  // first sampled column, first ring column
 
 	asm volatile("griddepcontrol.wait;" ::: "memory");  // launched with programmatic stream serialisation: nothing is touched before the predecessor is done
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && fix_count_next) *fix_count_next = 0u;  // the counter the next frame appends to
-	if (Xs + 1 > W - 1 || nr <= 0) return;  // (warp-uniform; there is no block-wide barrier in this kernel)
+	if (Xs + (EPI ? 2 : 1) > W - 1 || no <= 0) return;  // (warp-uniform; there is no block-wide barrier in this kernel)
 
 	const bool use_depth = REJ && Sw<FX>::depth(P);
 	const int nslots = (nr + 4 + LOOK + 1) / 2;  // ring rows Y0 - 2 .. Y0 + nr + 1 (+ LOOK) in boxes of two
@@ -375,7 +408,7 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	}
 	const int x0c = iclamp(c0, 0, W - 1), x1c = iclamp(c1, 0, W - 1);
 	const float u0 = ((float)x0c + 0.5f) / fW, u1 = ((float)x1c + 0.5f) / fW;  // tc_to_uv, taa.comp:131
-	const bool so0 = lane >= 1 && cv0, so1 = lane <= 30 && cv1;                  // the column is an output of this strip
+	const bool so0 = lane >= 1 && (!EPI || lane <= 30) && cv0, so1 = lane <= 30 && (!EPI || lane >= 1) && cv1;  // the column is an output of this strip
 	const bool al16 = (((unsigned long long)A.history_out.p | (unsigned long long)A.history_out.pitch | (unsigned long long)A.result.p | (unsigned long long)A.result.pitch) & 15ull) == 0ull;
 	const bool st16 = so0 && so1 && al16;
 
@@ -570,9 +603,42 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		    "}\n" ::"l"(ptr), "r"(q16), "r"(q0), "r"(q1), "r"(arg), "r"(ab), "r"(brg), "r"(bb)
 		    : "memory");
 	};
+	// ---- the sharpening epilogue: the resolved rows y - 1 (up) and y (centre) of the lane's two columns, as the rgba16f image holds them ----
+	F3 eUpA = {0.f, 0.f, 0.f}, eUpB = eUpA, eCeA = eUpA, eCeB = eUpA;
+	unsigned int o_fin = (unsigned int)(Y0 - A.final_img.y0) * (unsigned int)A.final_img.pitch + (unsigned int)x0c * 8u;  // offset of the CENTRE row
+	const float ek = A.epilogue_k;
+	const bool e16 = so0 && so1 && (((unsigned long long)A.final_img.p | (unsigned long long)A.final_img.pitch) & 15ull) == 0ull;
+	const unsigned int p16f = e16 ? 1u : 0u, p0f = (so0 && !e16) ? 1u : 0u, p1f = (so1 && !e16) ? 1u : 0u;
+	auto as_f3 = [](const unsigned int rg, const unsigned int b) { const float2 x = __half22float2(h2(rg)); F3 o; o.x = x.x; o.y = x.y; o.z = __low2float(h2(b)); return o; };
+	// the centre row gets its sharpened value: `dn` = the row below it (zero below the image, as an image load out of range returns)
+	auto emit_final = [&](const F3 dnA, const F3 dnB, const int yc) {
+		const F3 zero = {0.f, 0.f, 0.f};
+		// neighbours across lanes; at the image's left edge sharpen.comp clamps the coordinate (its own texel), CasFilter loads out of range (0);
+		// right of the last column both read out of range
+		F3 lfA, rtB;
+		lfA.x = __shfl_up_sync(0xffffffffu, eCeB.x, 1); lfA.y = __shfl_up_sync(0xffffffffu, eCeB.y, 1); lfA.z = __shfl_up_sync(0xffffffffu, eCeB.z, 1);
+		rtB.x = __shfl_down_sync(0xffffffffu, eCeA.x, 1); rtB.y = __shfl_down_sync(0xffffffffu, eCeA.y, 1); rtB.z = __shfl_down_sync(0xffffffffu, eCeA.z, 1);
+		if (c0 == 0) lfA = EPI == 1 ? eCeA : zero;
+		if (c1 == W - 1) rtB = zero;
+		const F3 rtA = c1 <= W - 1 ? eCeB : zero;
+		const F3 upA = yc == 0 ? (EPI == 1 ? eCeA : zero) : eUpA, upB = yc == 0 ? (EPI == 1 ? eCeB : zero) : eUpB;
+		if (yc >= Yo && yc < Yo + no) {
+			const F3 fa = sharpen_px<EPI>(upA, lfA, eCeA, rtA, dnA, ek), fb = sharpen_px<EPI>(upB, eCeA, eCeB, rtB, dnB, ek);
+			const __half2 arg = __floats2half2_rn(fa.x, fa.y), ab = __floats2half2_rn(fa.z, 1.0f), brg = __floats2half2_rn(fb.x, fb.y), bb = __floats2half2_rn(fb.z, 1.0f);
+			store_px(A.final_img.p, o_fin, p16f, p0f, p1f, *reinterpret_cast<const unsigned int*>(&arg), *reinterpret_cast<const unsigned int*>(&ab),
+			         *reinterpret_cast<const unsigned int*>(&brg), *reinterpret_cast<const unsigned int*>(&bb));
+		}
+	};
 	auto store_row = [&](const PixOut& a, const PixOut& b, const int i) {
-		store_px(A.history_out.p, o_hist, p16h, p0h, p1h, a.rg, a.bh, b.rg, b.bh);
-		store_px(A.result.p, o_res, p16r, p0r, p1r, a.rg, a.br, b.rg, b.br);
+		const bool own = !EPI || (Y0 + i >= Yo && Y0 + i < Yo + no);  // (the extra rows of the epilogue are resolved but not written)
+		store_px(A.history_out.p, o_hist, own ? p16h : 0u, own ? p0h : 0u, own ? p1h : 0u, a.rg, a.bh, b.rg, b.bh);
+		store_px(A.result.p, o_res, own ? p16r : 0u, own ? p0r : 0u, own ? p1r : 0u, a.rg, a.br, b.rg, b.br);
+		if (EPI) {
+			const F3 nA = as_f3(a.rg, a.br), nB = as_f3(b.rg, b.br);
+			if (i > 0) { emit_final(nA, nB, Y0 + i - 1); o_fin += (unsigned int)A.final_img.pitch; }
+			eUpA = eCeA; eUpB = eCeB; eCeA = nA; eCeB = nB;
+			if (i == nr - 1 && Y0 + i == H - 1) { const F3 zero = {0.f, 0.f, 0.f}; emit_final(zero, zero, Y0 + i); }  // the image's last row
+		}
 		if (DIAG) {
 			if (A.mask.p) {
 				if (so0) *reinterpret_cast<unsigned int*>(A.mask.p + o_mask) = a.mask;
@@ -893,12 +959,12 @@ bool tma_able(const Img& im) { return im.p && (((unsigned long long)im.p | (unsi
 
 // Rows per unit: the grid is (strip pairs) x ceil(band / R) CTAs on `resident` CTA slots; take the R whose last wave is fullest, weighted
 // by the per-unit overhead (tables, two extra sampled rows, the first window: ~2.5 rows' worth of instructions)
-int pick_rows(int nx, int band_rows, int resident) {
+int pick_rows(int nx, int band_rows, int resident, int rmax) {
 	static const int forced = [] { const char* s = getenv("TAA_STREAM_R"); return s ? atoi(s) : 0; }();
-	if (forced >= 2 && forced <= RMAX) return forced;
-	int best = RMAX;
+	if (forced >= 2 && forced <= rmax) return forced;
+	int best = rmax;
 	double best_eff = -1.0;
-	for (int r = 12; r <= RMAX; ++r) {
+	for (int r = 12; r <= rmax; ++r) {
 		const double n = (double)nx * ((band_rows + r - 1) / r);
 		const double waves = n / resident;
 		const double full = waves / (double)(long long)(waves + 0.999999);
@@ -908,10 +974,10 @@ int pick_rows(int nx, int band_rows, int resident) {
 	return best;
 }
 
-template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB>
+template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB, int EPI>
 cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const CUtensorMap& tmV, const CUtensorMap& tmD, unsigned int* fix_list, unsigned int* fix_count,
                            unsigned int* fix_count_next, float band, int num_sms, cudaStream_t stream) {
-	auto kern = taa_resolve_stream_kernel<REJ, ALPHA, DIAG, FX, MINB>;
+	auto kern = taa_resolve_stream_kernel<REJ, ALPHA, DIAG, FX, MINB, EPI>;
 	const int smem = (int)sizeof(WarpSmem<REJ>) * NWARP;
 	static int resident_per_sm[64] = {0};  // per device (the attribute and the occupancy are per device)
 	int dev = 0;
@@ -926,9 +992,10 @@ cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const C
 		if (e != cudaSuccess) return e;
 		resident_per_sm[dev] = nb > 0 ? nb : 1;
 	}
-	const int nstrips = (A.out_w + 1 + OWS - 1) / OWS;
+	// strips: 62 output columns starting at column -1 (the first strip's first column does not exist), or 60 starting at 0 with an epilogue
+	const int nstrips = EPI ? (A.out_w + OWS - 3) / (OWS - 2) : (A.out_w + 1 + OWS - 1) / OWS;
 	const int nx = (nstrips + NWARP - 1) / NWARP;
-	const int R = pick_rows(nx, A.band_rows, resident_per_sm[dev] * num_sms);
+	const int R = pick_rows(nx, A.band_rows, resident_per_sm[dev] * num_sms, EPI ? RMAX - 2 : RMAX);
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3(nx, (A.band_rows + R - 1) / R);
 	cfg.blockDim = dim3(32 * NWARP);
@@ -957,6 +1024,15 @@ bool stream_supports(const ResolveArgs& A) {
 	return true;
 }
 
+// The sharpening pass can ride in the resolve's epilogue when the call takes a plain variant of this kernel (no rejection switch) on a whole
+// frame and leaves nothing to the exact fix-up pass (no mask bound), which would have to patch the sharpened neighbours of the pixels it rewrites.
+bool stream_epilogue_ok(const ResolveArgs& A, bool fixup_all) {
+	const TaaParameters& P = A.ubo.param[0];
+	if (fixup_all || A.mask.p || P.mDepthCulling || P.mRejectOutside || P.mDynamicAntiGhosting) return false;
+	if (A.band_y0 != 0 || A.band_rows != A.out_h) return false;
+	return tuned_supports(A) && stream_supports(A);
+}
+
 cudaError_t launch_resolve_stream(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, bool fixup_all, int num_sms,
                                   cudaStream_t stream) {
 	const float band = fixup_all ? INFINITY : FIXUP_BAND_4K * fmaxf(1.0f, fmaxf((float)A.out_w / 3840.0f, (float)A.out_h / 3840.0f));
@@ -972,7 +1048,13 @@ cudaError_t launch_resolve_stream(const ResolveArgs& A, unsigned int* fix_list, 
 	static const int minb_env = [] { const char* v = getenv("TAA_STREAM_MINB"); return v ? atoi(v) : 0; }();
 	const bool fx3 = rej && alp && P.mDepthCulling && P.mRejectOutside && P.mDynamicAntiGhosting && P.mVelBasedAlpha && P.mLumaWeightingLottes &&
 	                 !P.mReduceBlendNearClamp && !A.ubo.mResetHistory;
-#define TAA_STREAM_GO(RJ, AL, DG, FX, MB) return launch_variant<RJ, AL, DG, FX, MB>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream)
+#define TAA_STREAM_GO(RJ, AL, DG, FX, MB) return launch_variant<RJ, AL, DG, FX, MB, 0>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream)
+	if (A.epilogue) {  // (stream_epilogue_ok() has admitted the call: a plain variant, nothing for the exact pass to decide)
+		if (A.epilogue == 1) return alp ? launch_variant<false, true, false, 0, 5, 1>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream)
+		                                : launch_variant<false, false, false, 0, 5, 1>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream);
+		return alp ? launch_variant<false, true, false, 0, 5, 2>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream)
+		           : launch_variant<false, false, false, 0, 5, 2>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream);
+	}
 	if (rej) {
 		if (fx3) { if (minb_env == 4) TAA_STREAM_GO(true, true, true, 1, 4); if (minb_env == 5) TAA_STREAM_GO(true, true, true, 1, 5); TAA_STREAM_GO(true, true, true, 1, 6); }
 		if (alp) TAA_STREAM_GO(true, true, true, 0, 6);
