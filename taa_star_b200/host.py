@@ -105,6 +105,14 @@ class TaaContext:
         fin = _image(final, 8)
         self._check(self._lib.taa_frame(self._h, C.byref(im), C.byref(uniforms), C.byref(chain), C.byref(fin), _stream_ptr(stream)), "taa_frame")
 
+    def frame_prepared(self, im: taa_resolve_images, uniforms: TaaUniforms, chain: taa_post_chain, fin, stream_ptr: int):
+        """taa_frame on pre-built argument blocks (fin = the taa_image of the final image): no per-call Python marshalling."""
+        self._check(self._lib.taa_frame(self._h, C.byref(im), C.byref(uniforms), C.byref(chain), C.byref(fin), stream_ptr), "taa_frame")
+
+    @staticmethod
+    def image(t, bpt: int = 8):
+        return _image(t, bpt)
+
     def sharpen(self, src, dst, factor: float, stream=None):
         pc = TaaSharpenPush(factor)
         a, b = _image(src, 8), _image(dst, 8)

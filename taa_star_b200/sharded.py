@@ -224,6 +224,58 @@ class ShardedTaa:
         return st
 
 
+def _whole_frame_reference(W, H, p, flags, dev, cfg_id, sh, halo, replicate):
+    """Runs frames 0 (history reset) and 1 of the synthetic sequence on this GPU alone over the whole W x H frame and through the sharded
+    pipeline; returns (ms per whole-frame step on one GPU, this rank's band identical bit for bit). Frame 1 reads the halo rows the
+    neighbours wrote in frame 0, so the comparison covers the exchange."""
+    from . import abi, configs, host
+    from .synth import SyntheticScene
+    L = sh.L
+    sc = SyntheticScene(W, H, device=dev, with_aux=False)
+    f = [sc.frame(0), sc.frame(1)]
+    ctx = host.TaaContext((W, H), flags=flags)
+    hist = [torch.zeros(H, W, 4, dtype=torch.float16, device=dev) for _ in range(2)]
+    res = torch.zeros(H, W, 4, dtype=torch.float16, device=dev)
+    u = [configs.uniforms_for(p, f[0].jitter_ndc, reset_history=True), configs.uniforms_for(p, f[1].jitter_ndc)]
+
+    def whole(i, par):
+        ctx.resolve(u[i], color=f[i].color, depth=f[i].depth, velocity=f[i].velocity, history_in=hist[par], history_out=hist[1 - par], result=res,
+                    history_depth=f[i - 1].depth if cfg_id == 3 else None)
+    whole(0, 0)
+    whole(1, 1)
+    torch.cuda.synchronize()
+    want_hist, want_res = hist[0][L.y0:L.y1].clone(), res[L.y0:L.y1].clone()
+    # the sharded pipeline on the same two frames (band rows + apron of the same inputs)
+    for i in range(2):
+        sh.step(u[i], f[i].color[L.iy0:L.iy1], f[i].depth[L.iy0:L.iy1], f[i].velocity[L.iy0:L.iy1], L.iy0,
+                history_depth=f[i - 1].depth[L.iy0:L.iy1] if cfg_id == 3 else None)
+    torch.cuda.synchronize()
+    got_hist = sh.hist[sh.parity][L.y0 - sh.hist_y0: L.y1 - sh.hist_y0]
+    same = bool(torch.equal(got_hist.view(torch.int16), want_hist.view(torch.int16)) and torch.equal(sh.result.view(torch.int16), want_res.view(torch.int16)))
+    # time the whole frame on one GPU (history ping-pong over the two frames; 2 x 20 B/px of inputs exceed the L2 from 4K upwards)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for k in range(4):
+        whole(k & 1, k & 1)
+    torch.cuda.synchronize()
+    n = 20
+    ev0.record()
+    for k in range(n):
+        whole(k & 1, k & 1)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / n
+    ctx.close()
+    del hist, res, f, sc
+    torch.cuda.empty_cache()
+    # leave the sharded pipeline as a fresh one would be
+    for h in sh.hist:
+        h.zero_()
+    if sh.parity:
+        sh.parity = 0
+    dist.barrier()
+    return ms, same
+
+
 # ---- bench (N > 1) ------------------------------------------------------------------------------------------------------------------
 def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
     from . import abi, configs
@@ -239,9 +291,17 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
     p = configs.config2_resolve() if cfg_id == 2 else configs.config3_full_chain()
     flags = abi.TAA_FLAG_EXACT if args.exact else 0
     halo = 20  # |v_y| <= 16 px guaranteed by the generator + 2 filter + 2 guard
-    sh = ShardedTaa(W, H, halo=halo, flags=flags, device=dev, apron=halo if cfg_id == 3 else 2)
+    replicate = bool(getattr(args, "replicate", False))
+    if W > 7680:
+        halo = halo * W // 7680  # (the synthetic motion and the fix-up band scale with the frame: same angular motion, more pixels)
+    sh = ShardedTaa(W, H, halo=halo, replicate=replicate, flags=flags, device=dev, apron=halo if cfg_id == 3 else 2)
     L = sh.L
     NSETS = 4
+    # ---- before anything is timed: the same two frames on ONE GPU (every rank does it for itself), (a) as the strong-scaling reference
+    # of this very frame size, (b) to check that this rank's band of the sharded result equals the whole-frame result bit for bit ----
+    single_ms, same = None, None
+    if not getattr(args, "no_verify", False):
+        single_ms, same = _whole_frame_reference(W, H, p, flags, dev, cfg_id, sh, halo, replicate)
     sc = SyntheticScene(W, H, device=dev, with_aux=False, rows=(L.iy0, L.iy1))
     frames = [sc.frame(n) for n in range(NSETS)]
     unis = [configs.uniforms_for(p, f.jitter_ndc) for f in frames]
@@ -369,17 +429,28 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_mpx = e2e_steps * px / float(dt.item()) / 1e6
     in_rows = L.iy1 - L.iy0
+    if same is not None:  # every rank's band must equal the whole-frame result
+        ok = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        same = bool(ok.item())
+        assert same, "a band of the sharded result differs from the whole-frame result"
+    lps = float(launches.item()) / max(args.steps, 1) / world  # launches per step and rank
     if rank == 0:
         line = {
             "metric": "resolved Mpixels/s", "value": round(mpx_s, 1), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 5), "host_enqueue_ms_per_step": round(host_ms_per_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": round(1e3 / ms_per_step, 1),
             "config": {"workload": f"{W}x{H} TAA resolve sharded in {world} row bands, BASELINE configs[3] (config {cfg_id} settings)",
-                       "arithmetic": "exact general kernel" if args.exact else "tuned kernel + exact fix-up pass", "halo_rows": halo,
-                       "exchange": "NCCL send/recv of 2 x halo rows of history per neighbour per frame, overlapped with the interior resolve",
+                       "arithmetic": "exact general kernel" if args.exact else ("tuned kernels + exact fix-up pass" if cfg_id == 3 else "tuned kernels alone (no mask bound: nothing for the exact fix-up pass to decide)"),
+                       "halo_rows": halo,
+                       "exchange": ("all-gather of the history bands (replicated history: correct for unbounded motion)" if replicate else
+                                    "NCCL send/recv of 2 x halo rows of history per neighbour per frame, overlapped with the interior resolve"),
                        "launch": graph_note,
                        "l2": f"inputs larger than L2: {NSETS} frame sets rotated, history ping-pong"},
-            "gpu_launches": int(launches.item()),
+            "gpu_launches": int(launches.item()), "gpu_launches_per_step_and_rank": round(lps, 2),
+            "single_gpu_same_frame_ms": round(single_ms, 5) if single_ms is not None else None,
+            "strong_scaling_efficiency_vs_same_frame": round(single_ms / ms_per_step / world, 4) if single_ms is not None else None,
+            "sharded_equals_whole_frame_bit_for_bit": same,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                          "peak_source": peak_src, "bytes_per_px": BYTES_PER_PX[cfg_id], "kernel": "taa_resolve (per GPU, whole sharded step incl. exchange)"},
             "cpu_baseline": None,
