@@ -1050,10 +1050,14 @@ cudaError_t launch_resolve_stream(const ResolveArgs& A, unsigned int* fix_list, 
 	                 !P.mReduceBlendNearClamp && !A.ubo.mResetHistory;
 #define TAA_STREAM_GO(RJ, AL, DG, FX, MB) return launch_variant<RJ, AL, DG, FX, MB, 0>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream)
 	if (A.epilogue) {  // (stream_epilogue_ok() has admitted the call: a plain variant, nothing for the exact pass to decide)
-		if (A.epilogue == 1) return alp ? launch_variant<false, true, false, 0, 5, 1>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream)
-		                                : launch_variant<false, false, false, 0, 5, 1>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream);
-		return alp ? launch_variant<false, true, false, 0, 5, 2>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream)
-		           : launch_variant<false, false, false, 0, 5, 2>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream);
+#define TAA_STREAM_EPI(AL, MB, EP) return launch_variant<false, AL, false, 0, MB, EP>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, stream)
+		static const int epi_minb = [] { const char* v = getenv("TAA_STREAM_EPI_MINB"); return v ? atoi(v) : 0; }();  // tuning aid
+		if (A.epilogue == 1) { if (alp) TAA_STREAM_EPI(true, 5, 1); TAA_STREAM_EPI(false, 5, 1); }
+		if (alp) TAA_STREAM_EPI(true, 5, 2);
+		if (epi_minb == 4) TAA_STREAM_EPI(false, 4, 2);
+		if (epi_minb == 6) TAA_STREAM_EPI(false, 6, 2);
+		TAA_STREAM_EPI(false, 5, 2);
+#undef TAA_STREAM_EPI
 	}
 	if (rej) {
 		if (fx3) { if (minb_env == 4) TAA_STREAM_GO(true, true, true, 1, 4); if (minb_env == 5) TAA_STREAM_GO(true, true, true, 1, 5); TAA_STREAM_GO(true, true, true, 1, 6); }

@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, replicate, q):
+def _worker(rank, world, port, replicate, q, geom=(96, 66, 9, 6, (2.0, 5.5), (-4.0, 3.0))):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -25,10 +25,10 @@ def _worker(rank, world, port, replicate, q):
         from taa_star_b200 import configs
         from taa_star_b200.sharded import BandLayout, HaloExchanger, band_of, gather_full_history
         from taa_star_b200.synth import SyntheticScene
-        W, H, halo = 96, 66, 9
+        W, H, halo, nframes, pan, mover = geom
         L = BandLayout(H, world, rank, halo)
         assert (L.y0, L.y1) == band_of(H, world, rank)
-        sc = SyntheticScene(W, H, pan_px=(2.0, 5.5), mover_px=(-4.0, 3.0), with_aux=False)
+        sc = SyntheticScene(W, H, pan_px=pan, mover_px=mover, with_aux=False)
         p = configs.config3_full_chain()
         xchg = HaloExchanger(L)
         # every rank also runs the whole frame (the reference result)
@@ -37,7 +37,7 @@ def _worker(rank, world, port, replicate, q):
         band_hist = torch.full((H, W, 4), float("nan"), dtype=torch.float16)
         band_hist[L.hy0:L.hy1] = 0
         prev_depth = None
-        for n in range(6):
+        for n in range(nframes):
             f = sc.frame(n)
             u = configs.uniforms_for(p, f.jitter_ndc, reset_history=(n == 0))
             col, dep, vel = f.color.numpy(), f.depth.numpy(), f.velocity.numpy()
@@ -90,6 +90,24 @@ def test_band_sharding_over_gloo(world, replicate):
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(msg == "ok" for _, msg in results), results
+
+
+def test_band_sharding_at_16k_width_over_gloo():
+    """BASELINE configs[3] names 15360x8640: the synthetic motion scales with the frame (the same angular motion covers twice the pixels of
+    8K), and so does the halo the sharded bench uses (sharded.bench_main: halo * W // 7680 = 40 rows). A strip of that width, two bands, a
+    vertical motion of 30 px per frame: the band with 40 halo rows reproduces the whole frame, and the exchange moves the right rows."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + 61
+    geom = (15360, 96, 40, 3, (12.0, 30.0), (-9.0, 14.0))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, False, q, geom)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
     assert all(msg == "ok" for _, msg in results), results
