@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -201,6 +202,7 @@ void taa_destroy(taa_ctx* c) {
 	for (void* p : c->scratch) if (p) cudaFree(p);
 	if (c->fix_list) cudaFree(c->fix_list);
 	if (c->fix_count) cudaFree(c->fix_count);
+	if (c->hints) cudaFree(c->hints);
 	delete c;
 }
 
@@ -342,6 +344,7 @@ int taa_frame(taa_ctx* c, const taa_resolve_images* images, const TaaUniforms* u
 	// variant of the streaming kernel with nothing left to the exact pass (stream_epilogue_ok). Without a sharpener an identity post-process
 	// is a copy: the resolve then writes its screen result straight into `final`.
 	const bool pp_identity = !post || (!chain->pp.zoom && chain->pp.splitX < 0 && !chain->pp.debugL_show);
+	static const int fuse_env = [] { const char* v = getenv("TAA_FUSED_CHAIN"); return v ? atoi(v) : -1; }();  // 0 / 1: A/B aid (default: see below)
 	if (!fxaa && pp_identity && (sharpen || post) && check_pitch(c, *final_img, d.out_width, 8, "final") == TAA_OK && !(c->desc.flags & TAA_FLAG_EXACT)) {
 		taa_resolve_images fim = *images;
 		if (!sharpen) {
@@ -353,7 +356,7 @@ int taa_frame(taa_ctx* c, const taa_resolve_images* images, const TaaUniforms* u
 			ResolveArgs A;
 			int r = build_resolve_args(c, &fim, u, A);
 			if (r != TAA_OK) return r;
-			if (stream_epilogue_ok(A, (c->desc.flags & TAA_FLAG_FIXUP_ALL) != 0) && final_img->data != fim.result.data && final_img->data != fim.history_out.data) {
+			if (fuse_env != 0 && stream_epilogue_ok(A, (c->desc.flags & TAA_FLAG_FIXUP_ALL) != 0) && final_img->data != fim.result.data && final_img->data != fim.history_out.data) {
 				fill_imgw(A.final_img, *final_img, d.out_height);
 				A.epilogue = chain->sharpener;
 				if (chain->sharpener == 1) A.epilogue_k = chain->sharpen.sharpeningFactor;

@@ -13,6 +13,8 @@ struct taa_ctx {
 	unsigned int* fix_list = nullptr;  // pixels the tuned kernel hands to the exact fix-up pass (one slot per band pixel)
 	unsigned int* fix_count = nullptr; // two counters, used alternately: call n appends to [n & 1] and zeroes [(n + 1) & 1]
 	int fix_parity = 0;
+	unsigned int* hints = nullptr;     // streaming kernel: units that were slow in the previous call (three rotating buffers)
+	int hint_phase = 0;
 	bool last_was_tuned = false;
 	long long launches = 0;            // kernels launched through this context
 	std::string last_error;

@@ -35,9 +35,15 @@ cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, i
 			cnt_next = c->fix_count + (c->fix_parity ^ 1);
 			c->fix_parity ^= 1;
 		}
+		const bool streaming = !tile && stream_supports(A);
+		if (streaming && !c->hints) {  // (a failed allocation only costs the ordering hint)
+			if (cudaMalloc(&c->hints, stream_hint_bytes()) == cudaSuccess) cudaMemsetAsync(c->hints, 0, stream_hint_bytes(), s);
+			else { c->hints = nullptr; cudaGetLastError(); }
+		}
 		cudaError_t e = tile ? launch_resolve_tuned(A, list, cnt, cnt_next, fixup_all, s)
-		                     : stream_supports(A) ? launch_resolve_stream(A, list, cnt, cnt_next, fixup_all, c->num_sms, s)
-		                                          : launch_resolve_strip(A, list, cnt, cnt_next, fixup_all, s);
+		                     : streaming ? launch_resolve_stream(A, list, cnt, cnt_next, fixup_all, c->num_sms, c->hints, c->hint_phase++, s)
+		                                 : launch_resolve_strip(A, list, cnt, cnt_next, fixup_all, s);
+		if (c->hint_phase >= 3 * 1024) c->hint_phase -= 3 * 1024;
 		if (e != cudaSuccess) return e;
 		*launched = 1;
 		if (need_fixup) {

@@ -26,8 +26,11 @@ cudaError_t launch_resolve_strip(const ResolveArgs& args, unsigned int* fix_list
 bool stream_supports(const ResolveArgs& args);
 // args.epilogue != 0 (the sharpening pass evaluated in the resolve's epilogue, written to args.final_img) is admissible for this call
 bool stream_epilogue_ok(const ResolveArgs& args, bool fixup_all);
+// hints: a device buffer of stream_hint_bytes() zeroed bytes owned by the context (or nullptr), hint_phase: a counter that advances by one per call —
+// the units that were slow in the previous call are started first (see "slow units first" in taa_resolve_stream.cu)
+size_t stream_hint_bytes();
 cudaError_t launch_resolve_stream(const ResolveArgs& args, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next,
-                                  bool fixup_all, int num_sms, cudaStream_t stream);
+                                  bool fixup_all, int num_sms, unsigned int* hints, int hint_phase, cudaStream_t stream);
 
 // follow-on passes, one kernel each as the reference dispatches them (taa_post.cu)
 struct PostImg { Img src; Img debug; ImgW dst; int w, h; };

@@ -118,6 +118,89 @@ __global__ void __launch_bounds__(256) blit_nearest_kernel(const __grid_constant
 	st_rgba16f(io.dst, x, y, ld_rgba16f(io.src, sx, sy, nullptr));
 }
 
+// ---- [sharpen | CAS] + identity post-process as a streaming pass --------------------------------------------------------------------------
+// The common case of the follow-on launch (no zoom box, no splitter, no debug view: post_process.comp only copies): a warp owns 64 columns,
+// a lane two adjacent texels (one 16-byte load and one 16-byte store per row), and walks down a run of rows with the rows above and below
+// the current one in registers — every texel is loaded once (plus two halo rows per run and one halo texel per warp edge), the horizontal
+// neighbours come over warp shuffles. The arithmetic is sharpen_at / cas_at's, value for value (the exact tests compare bit for bit).
+struct Px3 { float x, y, z; };
+__device__ __forceinline__ Px3 px3_of(unsigned int rg, unsigned int ba) {
+	const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rg));
+	Px3 o; o.x = a.x; o.y = a.y; o.z = __low2float(*reinterpret_cast<const __half2*>(&ba));
+	return o;
+}
+struct RowRec { Px3 a, b, ext; };  // the lane's two texels; ext: the texel beside the warp's 64 columns (lane 0: left of them, lane 31: right of them)
+
+template <int SHARPENER>
+__device__ __forceinline__ Px3 sharpened(const Px3 up, const Px3 lf, const Px3 ce, const Px3 rt, const Px3 dn, const float k) {
+	Px3 o;
+	if (SHARPENER == 1) {
+		o.x = fminf(fmaxf(ce.x + ((((4.0f * ce.x - lf.x) - rt.x) - up.x) - dn.x) * k, 0.f), 1.f);
+		o.y = fminf(fmaxf(ce.y + ((((4.0f * ce.y - lf.y) - rt.y) - up.y) - dn.y) * k, 0.f), 1.f);
+		o.z = fminf(fmaxf(ce.z + ((((4.0f * ce.z - lf.z) - rt.z) - up.z) - dn.z) * k, 0.f), 1.f);
+	} else {
+		const float mnG = min3f(min3f(lf.y, ce.y, rt.y), up.y, dn.y);
+		const float mxG = max3f(max3f(lf.y, ce.y, rt.y), up.y, dn.y);
+		float ampG = clampf(fminf(mnG, 1.0f - mxG) * prx_lo_rcp(mxG), 0.f, 1.f);
+		ampG = prx_lo_sqrt(ampG);
+		const float wG = ampG * k;
+		const float rcpWeight = prx_med_rcp(1.0f + 4.0f * wG);
+		o.x = clampf((up.x * wG + lf.x * wG + rt.x * wG + dn.x * wG + ce.x) * rcpWeight, 0.f, 1.f);
+		o.y = clampf((up.y * wG + lf.y * wG + rt.y * wG + dn.y * wG + ce.y) * rcpWeight, 0.f, 1.f);
+		o.z = clampf((up.z * wG + lf.z * wG + rt.z * wG + dn.z * wG + ce.z) * rcpWeight, 0.f, 1.f);
+	}
+	return o;
+}
+
+template <int SHARPENER>
+__global__ void __launch_bounds__(128) sharpen_rows_kernel(const __grid_constant__ PostImg io, const float k, const int run) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int w = io.w, h = io.h;
+	const int xw = (blockIdx.x * 4 + warp) * 64;  // first column of the warp
+	if (xw >= w) return;
+	const int x = xw + 2 * lane;                  // the lane's first column (w is even: both of its texels exist or neither does)
+	const bool live = x < w;
+	const int y0 = blockIdx.y * run, y1 = min(y0 + run, h);
+	const Px3 zero = {0.f, 0.f, 0.f};
+	// one image row as the stencil sees it: out of range reads as 0 (CasFilter loads unguarded, ffx_cas.h:429-437; sharpen.comp:21 clamps
+	// to `size`, so the row above the first is the first row itself, the row below the last is out of range)
+	auto load_row = [&](int y) -> RowRec {
+		RowRec r;
+		r.a = zero; r.b = zero; r.ext = zero;
+		if (SHARPENER == 1 && y < 0) y = 0;
+		if (y < 0 || y >= h) return r;
+		const unsigned char* row = io.src.p + (long long)(y - io.src.y0) * io.src.pitch;
+		if (live) {
+			const uint4 t = __ldg(reinterpret_cast<const uint4*>(row + (size_t)x * 8u));
+			r.a = px3_of(t.x, t.y); r.b = px3_of(t.z, t.w);
+		}
+		const int xe = lane == 0 ? xw - 1 : xw + 64;
+		if ((lane == 0 || lane == 31) && xe >= 0 && xe < w) {
+			const uint2 t = __ldg(reinterpret_cast<const uint2*>(row + (size_t)xe * 8u));
+			r.ext = px3_of(t.x, t.y);
+		}
+		return r;
+	};
+	RowRec up = load_row(y0 - 1), ce = load_row(y0);
+	for (int y = y0; y < y1; ++y) {
+		const RowRec dn = load_row(y + 1);
+		Px3 lf, rt;
+		lf.x = __shfl_up_sync(0xffffffffu, ce.b.x, 1); lf.y = __shfl_up_sync(0xffffffffu, ce.b.y, 1); lf.z = __shfl_up_sync(0xffffffffu, ce.b.z, 1);
+		rt.x = __shfl_down_sync(0xffffffffu, ce.a.x, 1); rt.y = __shfl_down_sync(0xffffffffu, ce.a.y, 1); rt.z = __shfl_down_sync(0xffffffffu, ce.a.z, 1);
+		if (lane == 0) lf = (SHARPENER == 1 && x == 0) ? ce.a : ce.ext;  // (sharpen.comp clamps the column to 0: its own texel)
+		if (lane == 31) rt = ce.ext;
+		if (x + 2 >= w) rt = zero;  // right of the last column: out of range
+		if (live) {
+			const Px3 fa = sharpened<SHARPENER>(up.a, lf, ce.a, ce.b, dn.a, k), fb = sharpened<SHARPENER>(up.b, ce.a, ce.b, rt, dn.b, k);
+			const __half2 arg = __floats2half2_rn(fa.x, fa.y), ab = __floats2half2_rn(fa.z, 1.0f), brg = __floats2half2_rn(fb.x, fb.y), bb = __floats2half2_rn(fb.z, 1.0f);
+			*reinterpret_cast<uint4*>(io.dst.p + (long long)(y - io.dst.y0) * io.dst.pitch + (size_t)x * 8u) =
+			    make_uint4(*reinterpret_cast<const unsigned int*>(&arg), *reinterpret_cast<const unsigned int*>(&ab), *reinterpret_cast<const unsigned int*>(&brg),
+			               *reinterpret_cast<const unsigned int*>(&bb));
+		}
+		up = ce; ce = dn;
+	}
+}
+
 inline dim3 grid2d(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
 
 }  // namespace
@@ -145,6 +228,20 @@ cudaError_t launch_post_process(const PostImg& io, const TaaPostProcessPush& pc,
 	return cudaGetLastError();
 }
 cudaError_t launch_sharpen_post(const PostImg& io, int sharpener, float sharpeningFactor, const TaaCasPush& cas, const TaaPostProcessPush& pc, cudaStream_t stream) {
+	// post_process.comp only copies (no zoom, no splitter, no debug view) and the rows can be moved 16 bytes at a time: the streaming pass
+	const bool identity = !pc.zoom && pc.splitX < 0 && !pc.debugL_show;
+	const bool aligned = (io.w & 1) == 0 && (((unsigned long long)io.src.p | (unsigned long long)io.src.pitch | (unsigned long long)io.dst.p | (unsigned long long)io.dst.pitch) & 15ull) == 0ull;
+	if (identity && aligned && (sharpener == 1 || sharpener == 2)) {
+		const int run = 32;  // rows per warp: two halo rows per 32
+		const dim3 grid((io.w + 255) / 256, (io.h + run - 1) / run);
+		if (sharpener == 1) sharpen_rows_kernel<1><<<grid, 128, 0, stream>>>(io, sharpeningFactor, run);
+		else {
+			float peak;
+			memcpy(&peak, &cas.const1[0], 4);
+			sharpen_rows_kernel<2><<<grid, 128, 0, stream>>>(io, peak, run);
+		}
+		return cudaGetLastError();
+	}
 	dim3 b(32, 8);
 	if (sharpener == 1) post_process_kernel<1><<<grid2d(io.w, io.h, b), b, 0, stream>>>(io, pc, sharpeningFactor);
 	else {
