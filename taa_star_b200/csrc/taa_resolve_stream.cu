@@ -291,12 +291,10 @@ __device__ __forceinline__ PixOut resolve_pixel(const ResolveArgs& A, const KCon
 // The general history sample (taa.comp:441-514 through the sampler, re-associated): the 4 x 4 footprint gathered through L1.
 // ring = OR of the alpha words of the 6 x 6 texels around the footprint (all ones where they are not all in reach).
 template <bool REJ>
-__device__ __forceinline__ void gather_history(const ResolveArgs& A, const float hu, const float hv, const int W, const int H, const float fW, const float fH,
-                                               const float invw, const float invh, const int hlo, const int hhi, float& hsr, float& hsg, float& hsb, float& hsa,
-                                               unsigned int& ring, int& kx, int& K) {
+__device__ __forceinline__ void gather_history(const ResolveArgs& A, const AxisW& ax, const AxisW& ay, const int W, const int H, const int hlo, const int hhi, float& hsr,
+                                               float& hsg, float& hsb, float& hsa, unsigned int& ring) {
 	unsigned int* st = A.status;
-	const AxisW ax = catmull_axis(hu, fW, invw), ay = catmull_axis(hv, fH, invh);
-	kx = ax.k; K = ay.k - 1;
+	const int kx = ax.k, K = ay.k - 1;
 	const int rg = REJ ? 1 : 0;
 	const bool interior = kx - 1 - rg >= 0 && kx + 2 + rg <= W - 1 && K - rg >= hlo && K + 3 + rg <= hhi;
 	uint2 q[16];
@@ -368,7 +366,7 @@ __device__ __forceinline__ unsigned int smid() { unsigned int t; asm volatile("m
 
 // How a launch cuts its band into units: row blocks 0 .. nbig - 1 are R rows high, the blocks after them Rs (<= R) rows: the CTAs are dispatched in
 // index order, so the last wave consists of short units and the launch ends on a finer grain (decreasing chunk sizes, as in guided self-scheduling).
-struct UnitGeo { int nx, R, nbig, Rs, gen_pf; };
+struct UnitGeo { int nx, R, nbig, Rs; };
 
 template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB, int EPI>
 __global__ void __launch_bounds__(32 * NWARP, MINB)
@@ -886,16 +884,19 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 			vo00 = (unsigned int)iclamp(L0.i0 - Xb, 0, RWT - 1) * 8u; vo01 = (unsigned int)iclamp(L0.i1 - Xb, 0, RWT - 1) * 8u; va0 = L0.a;
 			vo10 = (unsigned int)iclamp(L1.i0 - Xb, 0, RWT - 1) * 8u; vo11 = (unsigned int)iclamp(L1.i1 - Xb, 0, RWT - 1) * 8u; va1 = L1.a;
 		}
-		auto general_pixel = [&](const int i, const unsigned int o0, const unsigned int o1, const float a, const float u, const F3 cur, const F3 S1, const F3 S2,
-		                         const float depth, const bool movers_near) -> PixOut {
+		struct Pos { float hu, hv, v, velz; bool movC; };  // where the pixel's history lies
+		// ---- getHistoryPosition (taa.comp:391-438), exact ----
+		auto history_pos = [&](const int i, const unsigned int o0, const unsigned int o1, const float a, const float u) -> Pos {
 			const uint4 tb = sm.tabB[i + 1];
 			const unsigned int r0 = tb.x & 0xffffu, r1 = tb.x >> 16;
-			const float ra = __uint_as_float(tb.y), v = __uint_as_float(tb.z);
-			// ---- getHistoryPosition (taa.comp:391-438), exact ----
+			const float ra = __uint_as_float(tb.y);
+			Pos o;
+			o.v = __uint_as_float(tb.z);
 			const uint2 vt00 = *reinterpret_cast<const uint2*>(vraw + (r0 + o0)), vt10 = *reinterpret_cast<const uint2*>(vraw + (r0 + o1));
 			const uint2 vt01 = *reinterpret_cast<const uint2*>(vraw + (r1 + o0)), vt11 = *reinterpret_cast<const uint2*>(vraw + (r1 + o1));
-			float velx, vely, velz = 0.f;
-			bool movC = false;
+			float velx, vely;
+			o.velz = 0.f;
+			o.movC = false;
 			bool same = vt00.x == vt10.x && vt00.x == vt01.x && vt00.x == vt11.x && finite2(vt00.x);
 			if (REJ) same = same && vt00.y == vt10.y && vt00.y == vt01.y && vt00.y == vt11.y && finite2(vt00.y);
 			if (same) {  // lerp(p, p, w) == p + w * 0 == p for finite p
@@ -903,8 +904,8 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 				velx = xy.x; vely = xy.y;
 				if (REJ) {
 					const float2 zw = __half22float2(h2(vt00.y));
-					velz = zw.x;
-					movC = (fabsf(velx) > 1e-5f || fabsf(vely) > 1e-5f) && (fabsf(zw.y) >= 0.5f);
+					o.velz = zw.x;
+					o.movC = (fabsf(velx) > 1e-5f || fabsf(vely) > 1e-5f) && (fabsf(zw.y) >= 0.5f);
 				}
 			} else {
 				const float2 a00 = __half22float2(h2(vt00.x)), a10 = __half22float2(h2(vt10.x)), a01 = __half22float2(h2(vt01.x)), a11 = __half22float2(h2(vt11.x));
@@ -912,28 +913,23 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 				vely = lerpf(lerpf(a00.y, a10.y, a), lerpf(a01.y, a11.y, a), ra);
 				if (REJ) {
 					const float2 b00 = __half22float2(h2(vt00.y)), b10 = __half22float2(h2(vt10.y)), b01 = __half22float2(h2(vt01.y)), b11 = __half22float2(h2(vt11.y));
-					velz = lerpf(lerpf(b00.x, b10.x, a), lerpf(b01.x, b11.x, a), ra);
+					o.velz = lerpf(lerpf(b00.x, b10.x, a), lerpf(b01.x, b11.x, a), ra);
 					const float velw = lerpf(lerpf(b00.y, b10.y, a), lerpf(b01.y, b11.y, a), ra);
-					movC = (fabsf(velx) > 1e-5f || fabsf(vely) > 1e-5f) && (fabsf(velw) >= 0.5f);
+					o.movC = (fabsf(velx) > 1e-5f || fabsf(vely) > 1e-5f) && (fabsf(velw) >= 0.5f);
 				}
 			}
-			const float hu = u - velx, hv = v - vely;
-			float hsr, hsg, hsb, hsa;
-			unsigned int ring;
-			int kx, K;
-			gather_history<REJ>(A, hu, hv, W, H, fW, fH, invw, invh, hlo, hhi, hsr, hsg, hsb, hsa, ring, kx, K);
-			// The next rows' footprints lie (motion varies slowly) a row further down each: the row that joins them is requested ahead of time, so
-			// that the gather finds it in the cache instead of waiting for DRAM once per pixel row (the uniform rows do the same from their table).
-			if (geo.gen_pf & 3) {
-				const unsigned char* pp = hbase + ((unsigned int)(iclamp(K + 3 + (geo.gen_pf >> 4), hlo, hhi) - A.history_in.y0) * hpitch + (unsigned int)iclamp(kx, 0, W - 1) * 8u);
-				if (geo.gen_pf & 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
-				else asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
-			}
+			o.hu = u - velx; o.hv = o.v - vely;
+			return o;
+		};
+		struct HS { float r, g, b, a; unsigned int ring; };  // the filtered history sample
+		// everything after the history sample
+		auto finish_pixel = [&](const Pos& ps, const HS& hs, const float u, const F3 cur, const F3 S1, const F3 S2, const float depth, const bool movers_near) -> PixOut {
+			const float hu = ps.hu, hv = ps.hv, v = ps.v;
 			bool rejected = false, movement = false;
 			if (REJ) {
 				if (Sw<FX>::outside(P) && (hu < 0.f || hv < 0.f || hu >= 1.f || hv >= 1.f)) rejected = true;
 				if (Sw<FX>::antighost(P)) {
-					movement = movC;
+					movement = ps.movC;
 					// the four other taps of the movement test (taa.comp:796-806): where no texel within two of the strip's recent rows carries
 					// velocity.w, every tap's w is exactly 0
 					if (!movement && movers_near) {
@@ -946,13 +942,13 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 					}
 				}
 				if (use_depth) {
-					const float expected = depth - velz;
+					const float expected = depth - ps.velz;
 					const float hd = fetch_r32f(A.history_depth, W, H, (int)(hu * fW), (int)(hv * fH), st);
 					if (fabsf(hd - expected) > 0.1f * (1.0f - hd)) rejected = true;
 				}
 			}
-			PixOut o = resolve_pixel<REJ, ALPHA, DIAG, FX>(A, kc, fix_band, cur, S1, S2, hsr, hsg, hsb, hsa, rejected, movement, movC, u - hu, v - hv);
-			if (REJ && o.check_ring && (ring & 0x7fff0000u)) o.uncertain = true;
+			PixOut o = resolve_pixel<REJ, ALPHA, DIAG, FX>(A, kc, fix_band, cur, S1, S2, hs.r, hs.g, hs.b, hs.a, rejected, movement, ps.movC, u - hu, v - hv);
+			if (REJ && o.check_ring && (hs.ring & 0x7fff0000u)) o.uncertain = true;
 			return o;
 		};
 		auto general_row = [&](const int i) {  // (the rolling box is kept in slot 0: the general rows move it there, a few MOVs do not matter here)
@@ -965,16 +961,49 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 			if (use_depth) d = *reinterpret_cast<const float2*>(sm.dt + ring_row(Y0 + i, Y0 - 2, NR) * DROWB + (unsigned int)(2 * lane + (Xs & 3)) * 4u);
 			// velocity rows up to Y0 + i + 4 (+ 1) have been voted: bits 0 .. 7 cover rows y - 2 .. y + 2 of both rows of the step
 			const bool movers_near = REJ && (wrows & 0xffu) != 0u;
-			const PixOut oa = general_pixel(i, vo00, vo01, va0, u0, ca, S1a, S2a, d.x, movers_near);
-			const PixOut ob = general_pixel(i, vo10, vo11, va1, u1, cb, S1b, S2b, d.y, movers_near);
+			const Pos pa = history_pos(i, vo00, vo01, va0, u0), pb = history_pos(i, vo10, vo11, va1, u1);
+			HS ha, hb;
+			// The usual case under smoothly varying motion: the two footprints are interior, start on the same row and one column apart (columns
+			// k - 1 .. k + 3 cover both). If that holds for every lane, the 4 x 5 texels are requested in one batch and each is converted once; the
+			// arithmetic per pixel is the one of gather_history (same weights, same order of summation: same bits).
+			const AxisW ax0 = catmull_axis(pa.hu, fW, invw), ay0 = catmull_axis(pa.hv, fH, invh);
+			const AxisW ax1 = catmull_axis(pb.hu, fW, invw), ay1 = catmull_axis(pb.hv, fH, invh);
+			const int kx = ax0.k, K = ay0.k - 1;
+			const bool paired = !REJ && ax1.k == kx + 1 && ay1.k == ay0.k && kx - 1 >= 0 && kx + 3 <= W - 1 && K >= hlo && K + 3 <= hhi;
+			if (__all_sync(0xffffffffu, paired)) {
+				const unsigned char* p = hbase + ((unsigned int)(K - A.history_in.y0) * hpitch + (unsigned int)(kx - 1) * 8u);
+				uint2 q[20];
+#pragma unroll
+				for (int r = 0; r < 4; ++r) {
+					const uint2* hp = reinterpret_cast<const uint2*>(p + r * hpitch);
+#pragma unroll
+					for (int c = 0; c < 5; ++c) q[5 * r + c] = __ldg(hp + c);
+				}
+				HR fa[4], fb[4];
+#pragma unroll
+				for (int r = 0; r < 4; ++r) hfilter_pair<false>(q[5 * r], q[5 * r + 1], q[5 * r + 2], q[5 * r + 3], q[5 * r + 4], ax0.w, ax1.w, fa[r], fb[r]);
+				ha.r = fmaf(ay0.w[3], fa[3].r, fmaf(ay0.w[2], fa[2].r, fmaf(ay0.w[1], fa[1].r, ay0.w[0] * fa[0].r)));
+				ha.g = fmaf(ay0.w[3], fa[3].g, fmaf(ay0.w[2], fa[2].g, fmaf(ay0.w[1], fa[1].g, ay0.w[0] * fa[0].g)));
+				ha.b = fmaf(ay0.w[3], fa[3].b, fmaf(ay0.w[2], fa[2].b, fmaf(ay0.w[1], fa[1].b, ay0.w[0] * fa[0].b)));
+				hb.r = fmaf(ay1.w[3], fb[3].r, fmaf(ay1.w[2], fb[2].r, fmaf(ay1.w[1], fb[1].r, ay1.w[0] * fb[0].r)));
+				hb.g = fmaf(ay1.w[3], fb[3].g, fmaf(ay1.w[2], fb[2].g, fmaf(ay1.w[1], fb[1].g, ay1.w[0] * fb[0].g)));
+				hb.b = fmaf(ay1.w[3], fb[3].b, fmaf(ay1.w[2], fb[2].b, fmaf(ay1.w[1], fb[1].b, ay1.w[0] * fb[0].b)));
+				ha.a = 0.f; hb.a = 0.f; ha.ring = 0u; hb.ring = 0u;
+			} else {
+				gather_history<REJ>(A, ax0, ay0, W, H, hlo, hhi, ha.r, ha.g, ha.b, ha.a, ha.ring);
+				gather_history<REJ>(A, ax1, ay1, W, H, hlo, hhi, hb.r, hb.g, hb.b, hb.a, hb.ring);
+			}
+			const PixOut oa = finish_pixel(pa, ha, u0, ca, S1a, S2a, d.x, movers_near);
+			const PixOut ob = finish_pixel(pb, hb, u1, cb, S1b, S2b, d.y, movers_near);
 			store_row(oa, ob, i);
 		};
 		if (i & 1) { QA[0] = QA[1]; QB[0] = QB[1]; CURA[0] = CURA[1]; CURB[0] = CURB[1]; }  // (never: the uniform rows are left at a step boundary)
 		while (i < nr) {
 			if (!begun) step_begin(i);
 			begun = false;
-			general_row(i);
-			if (i + 1 < nr) general_row(i + 1);
+#pragma unroll 1
+			for (int r = 0; r < 2; ++r)  // (one copy of the row in the instruction stream: the general rows were short of instruction cache)
+				if (i + r < nr) general_row(i + r);
 			step_end(i);
 			i += 2;
 		}
@@ -1090,9 +1119,8 @@ cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const C
 	static const int tail_env = [] { const char* v = getenv("TAA_STREAM_TAIL"); return v ? atoi(v) : -1; }();   // tuning aids
 	const int tail_pct = tail_env >= 0 ? tail_env : (hints_on ? 20 : 0);
 	static const int rs_env = [] { const char* v = getenv("TAA_STREAM_RS"); return v ? atoi(v) : 0; }();
-	static const int gen_pf = [] { const char* v = getenv("TAA_STREAM_GENPF"); return v ? atoi(v) : 0; }();
 	UnitGeo geo;
-	geo.nx = nx; geo.R = R; geo.gen_pf = gen_pf;
+	geo.nx = nx; geo.R = R;
 	geo.Rs = rs_env >= 2 && rs_env <= R ? rs_env : max(2, (R / 2 + 1) & ~1);
 	geo.nbig = tail_pct > 0 ? (int)(((long long)A.band_rows * (100 - min(tail_pct, 100)) / 100) / R) : (A.band_rows + R - 1) / R;
 	const int rest = max(0, A.band_rows - geo.nbig * R);
