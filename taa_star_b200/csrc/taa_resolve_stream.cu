@@ -44,7 +44,11 @@ constexpr int RWT = 72;                     // ring row: image columns Xb .. Xb 
 constexpr unsigned int ROWB = RWT * 8u;
 constexpr int SROWS = 2;                    // rows per slot = per TMA box
 constexpr int RMAX = 30;                    // output rows per unit: one 32-entry row table covers rows Y0 - 1 .. Y0 + 30
-constexpr int NWARP = 2;                    // warps (independent strips) per CTA
+#ifndef TAA_STREAM_NWARP
+#define TAA_STREAM_NWARP 2
+#endif
+constexpr int NWARP = TAA_STREAM_NWARP;     // warps (independent strips) per CTA; MINB below counts PAIRS of warps per SM. (One warp per CTA frees a slot the
+                                            // moment its strip is done, but measured slower on B200: 0.1025 against 0.0990 ms, 4K pan + mover.)
 constexpr int PFD = 3;                      // L2 prefetch distance of the history rows, in rows beyond the one requested (0: off)
 constexpr int DW = 80;                      // depth ring row: columns Xd .. Xd + 79, Xd = Xs rounded down to a multiple of four (a box starts on 16 bytes)
 constexpr unsigned int DROWB = DW * 4u;
@@ -369,7 +373,7 @@ __device__ __forceinline__ unsigned int smid() { unsigned int t; asm volatile("m
 struct UnitGeo { int nx, R, nbig, Rs; };
 
 template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB, int EPI>
-__global__ void __launch_bounds__(32 * NWARP, MINB)
+__global__ void __launch_bounds__(32 * NWARP, MINB * 2 / NWARP)
 taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmV,
                           const __grid_constant__ CUtensorMap tmD, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
                           unsigned int* __restrict__ fix_count_next, const float fix_band, const UnitGeo geo, const unsigned int rt_zero,
@@ -868,10 +872,16 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 
 	if (i < nr) {
 		// ================================ general rows ================================
-		if (hint_out && lane == 0 && atomicCAS(&hint_out[2u + HINT_N + cta], 0u, 0xffffffffu) == 0u) {  // a slow unit: the next frame starts it first
-			const unsigned int slot = atomicAdd(&hint_out[0], 1u);
-			if (slot < HINT_N) hint_out[2u + slot] = cta;
-			hint_out[2u + HINT_N + cta] = slot < HINT_N ? slot + 1u : 0u;
+		// a slow unit: the next frame starts it first — and its left and right neighbours with it (an edge that moves on by a strip is then
+		// expected there; a hinted unit that turns out fast costs nothing, it just runs early)
+		if (hint_out && lane < 3) {
+			const int nb = bx + (lane == 0 ? 0 : lane == 1 ? -1 : 1);
+			const unsigned int u = (unsigned int)(by * geo.nx + nb);
+			if (nb >= 0 && nb < geo.nx && atomicCAS(&hint_out[2u + HINT_N + u], 0u, 0xffffffffu) == 0u) {
+				const unsigned int slot = atomicAdd(&hint_out[0], 1u);
+				if (slot < HINT_N) hint_out[2u + slot] = u;
+				hint_out[2u + HINT_N + u] = slot < HINT_N ? slot + 1u : 0u;
+			}
 		}
 #ifdef TAA_STREAM_TRACE
 		tr_general = i;
@@ -1100,7 +1110,7 @@ cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const C
 	if (!resident_per_sm[dev]) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e != cudaSuccess) return e;
-		cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100 * MINB * (smem + 1024) / (228 * 1024) + 2);
+		cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100 * (MINB * 2 / NWARP) * (smem + 1024) / (228 * 1024) + 2);
 		int nb = 0;
 		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * NWARP, smem);
 		if (e != cudaSuccess) return e;
