@@ -29,8 +29,18 @@ bool stream_epilogue_ok(const ResolveArgs& args, bool fixup_all);
 // hints: a device buffer of stream_hint_bytes() zeroed bytes owned by the context (or nullptr), hint_phase: a counter that advances by one per call —
 // the units that were slow in the previous call are started first (see "slow units first" in taa_resolve_stream.cu)
 size_t stream_hint_bytes();
+// Row bands without a per-frame collective ("PEER variants" in taa_resolve_stream.cu): side 0 = the band above, 1 = the band below.
+struct StreamPeers {
+	unsigned char* nb_hist[2];   // the neighbour's history buffer with the parity of args.history_out, mapped into this process (nullptr: no neighbour)
+	long long nb_pitch[2];
+	int nb_y0[2];                // global row in the neighbour's buffer row 0
+	int nb_band_rows[2];         // output rows the neighbour resolves
+	unsigned int* nb_flags[2];   // the neighbour's flag block (TAA_BAND_FLAG_WORDS words), mapped
+	unsigned int* flags;         // this band's flag block
+	int halo, q, wait;           // halo rows; parity of the history buffer being written; 0: the first frame of a sequence (nothing to wait for)
+};
 cudaError_t launch_resolve_stream(const ResolveArgs& args, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next,
-                                  bool fixup_all, int num_sms, unsigned int* hints, int hint_phase, cudaStream_t stream);
+                                  bool fixup_all, int num_sms, unsigned int* hints, int hint_phase, const StreamPeers* peers, cudaStream_t stream);
 
 // follow-on passes, one kernel each as the reference dispatches them (taa_post.cu)
 struct PostImg { Img src; Img debug; ImgW dst; int w, h; };

@@ -370,14 +370,44 @@ __device__ __forceinline__ unsigned int smid() { unsigned int t; asm volatile("m
 
 // How a launch cuts its band into units: row blocks 0 .. nbig - 1 are R rows high, the blocks after them Rs (<= R) rows: the CTAs are dispatched in
 // index order, so the last wave consists of short units and the launch ends on a finer grain (decreasing chunk sizes, as in guided self-scheduling).
-struct UnitGeo { int nx, R, nbig, Rs; };
+struct UnitGeo { int nx, R, nbig, Rs, ny, nbt, nbb; };  // ny row blocks; the first nbt / last nbb of them are the band's boundary blocks (peer mode)
 
-template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB, int EPI>
+// ---- row bands without a per-frame collective (PEER variants) ------------------------------------------------------------------------------
+// A band's first / last `halo` rows of history_out are what the neighbour above / below reads as the halo of its history_in in the next frame.
+// The units that resolve those rows (the boundary blocks) store them a second time, straight into the neighbour's buffer (peer-mapped memory
+// over NVLink), and then signal a counter in the neighbour's flag block: st ... ; fence.sys ; red.add on the peer word. The same units are the
+// only ones of the neighbour's NEXT frame that read those rows: they wait (ld.acquire.sys) for the counter to reach the number of signalling
+// warps before they touch the history. Boundary blocks are dispatched first, so that the neighbour's flag is complete long before its next
+// frame starts; in the steady state nobody spins. The words are indexed by the parity q of the history buffer being written:
+//   flags[2 s + q]     signals received from side s (0: the band above, 1: the band below) for buffers of parity q
+//   flags[4 + 2 s + q] this band's own boundary warps of side s that are done with the frame writing parity q
+// The last boundary warp of a side resets the word its side waited on (parity q ^ 1) before it signals: the neighbour cannot signal that word
+// again before it has seen all of this frame's signals. A neighbour's stores into the parity-q halo can only begin after it has seen this
+// band's signals of the frame before, i.e. after every reader of that halo is done (write-after-read).
+struct PeerArgs {
+	unsigned char* nb_hist[2];   // the neighbours' history buffer of the parity being written, mapped into this process (nullptr: no neighbour)
+	long long nb_pitch[2];
+	int nb_y0[2];
+	unsigned int* nb_flags[2];   // the neighbours' flag blocks
+	unsigned int* flags;         // this band's flag block
+	unsigned int expect[2];      // signals per frame from side s
+	unsigned int mine[2];        // boundary warps of this band on side s
+	int halo, q, wait;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+	unsigned int v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB, int EPI, bool PEER>
 __global__ void __launch_bounds__(32 * NWARP, MINB * 2 / NWARP)
 taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmV,
                           const __grid_constant__ CUtensorMap tmD, unsigned int* __restrict__ fix_list, unsigned int* __restrict__ fix_count,
                           unsigned int* __restrict__ fix_count_next, const float fix_band, const UnitGeo geo, const unsigned int rt_zero,
-                          const unsigned int* __restrict__ hint_in, unsigned int* __restrict__ hint_out, unsigned int* __restrict__ hint_clear, const unsigned int hint_sig) {
+                          const unsigned int* __restrict__ hint_in, unsigned int* __restrict__ hint_out, unsigned int* __restrict__ hint_clear, const unsigned int hint_sig,
+                          const __grid_constant__ PeerArgs peer) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	using C = Cfg<REJ>;
 	constexpr int NSLOT = C::NSLOT, NR = C::NR, LOOK = C::LOOK;
@@ -409,7 +439,12 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		}
 		if (threadIdx.x == 0) hint_clear[2u + HINT_N + cta] = 0u;
 	}
-	const int bx = (int)(cta % (unsigned int)geo.nx), by = (int)(cta / (unsigned int)geo.nx);
+	const int bx = (int)(cta % (unsigned int)geo.nx);
+	int by = (int)(cta / (unsigned int)geo.nx);
+	if (PEER) {  // dispatch order: the top boundary blocks, the bottom boundary blocks, then the interior
+		if (by >= geo.nbt) by = by < geo.nbt + geo.nbb ? geo.ny - geo.nbb + (by - geo.nbt) : by - geo.nbb;
+	}
+	const bool side_top = PEER && peer.nb_hist[0] != nullptr && by < geo.nbt, side_bot = PEER && peer.nb_hist[1] != nullptr && by >= geo.ny - geo.nbb;
 	const int strip = bx * NWARP + warp;
 	// rows this unit owns (writes); with a sharpening epilogue it also resolves the row above and the row below them, whose values the
 	// plus-shaped stencil needs (whole frames only: the follow-on passes do not run on bands)
@@ -421,6 +456,21 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	const int Xs = strip * STEP_X - 2, Xb = Xs - 2;  // first sampled column, first ring column
 
 	if (Xs + (EPI ? 2 : 1) > W - 1 || no <= 0) return;  // (warp-uniform; there is no block-wide barrier in this kernel)
+	if (PEER && peer.wait && (side_top || side_bot)) {
+		// the halo rows this unit may read were stored by the neighbour's boundary warps during the previous frame: all of them must have signalled
+		if (lane == 0) {
+			const long long t0 = clock64();
+			for (int sd = 0; sd < 2; ++sd) {
+				if (!(sd == 0 ? side_top : side_bot)) continue;
+				const unsigned int* f = peer.flags + (2 * sd + (peer.q ^ 1));
+				while (ld_acquire_sys(f) < peer.expect[sd]) {
+					__nanosleep(64);
+					if (clock64() - t0 > (1ll << 32)) { if (st) atomicOr(st, 2u); break; }  // (~2 s: reported as a peer time-out, never a hang)
+				}
+			}
+		}
+		__syncwarp();
+	}
 #ifdef TAA_STREAM_TRACE
 	const unsigned long long tr_t0 = gtime();
 	int tr_general = 0xffff;
@@ -696,6 +746,13 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	auto store_row = [&](const PixOut& a, const PixOut& b, const int i) {
 		const bool own = !EPI || (Y0 + i >= Yo && Y0 + i < Yo + no);  // (the extra rows of the epilogue are resolved but not written)
 		store_px(A.history_out.p, o_hist, own ? p16h : 0u, own ? p0h : 0u, own ? p1h : 0u, a.rg, a.bh, b.rg, b.bh);
+		if (PEER) {  // the band's first / last halo rows go to the neighbour's halo as well
+			const int g = Y0 + i;
+			if (side_top && g < A.band_y0 + peer.halo)
+				store_px(peer.nb_hist[0], (unsigned int)(g - peer.nb_y0[0]) * (unsigned int)peer.nb_pitch[0] + (unsigned int)x0c * 8u, p16h, p0h, p1h, a.rg, a.bh, b.rg, b.bh);
+			if (side_bot && g >= A.band_y0 + A.band_rows - peer.halo)
+				store_px(peer.nb_hist[1], (unsigned int)(g - peer.nb_y0[1]) * (unsigned int)peer.nb_pitch[1] + (unsigned int)x0c * 8u, p16h, p0h, p1h, a.rg, a.bh, b.rg, b.bh);
+		}
 		store_px(A.result.p, o_res, own ? p16r : 0u, own ? p0r : 0u, own ? p1r : 0u, a.rg, a.br, b.rg, b.br);
 		if (EPI) {
 			const F3 nA = as_f3(a.rg, a.br), nB = as_f3(b.rg, b.br);
@@ -1019,6 +1076,23 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		}
 	}
 
+	if (PEER && (side_top || side_bot)) {
+		__threadfence_system();  // every lane's stores (local and peer) are ordered before the signal
+		__syncwarp();
+		if (lane == 0) {
+			for (int sd = 0; sd < 2; ++sd) {
+				if (!(sd == 0 ? side_top : side_bot)) continue;
+				unsigned int* done = peer.flags + (4 + 2 * sd + peer.q);
+				if (atomicAdd(done, 1u) == peer.mine[sd] - 1u) {  // the side's last warp: the word the side waited on is free for the frame after the next
+					peer.flags[2 * sd + (peer.q ^ 1)] = 0u;
+					*done = 0u;
+					__threadfence_system();
+				}
+				// this band is side (1 - sd) of that neighbour
+				asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(peer.nb_flags[sd] + (2 * (1 - sd) + peer.q)) : "memory");
+			}
+		}
+	}
 #ifdef TAA_STREAM_TRACE
 	if (lane == 0) {
 		const unsigned int u = (cta * NWARP + warp) & 16383u;
@@ -1098,10 +1172,35 @@ int pick_rows(int nx, int band_rows, int resident, int rmax) {
 	return best;
 }
 
-template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB, int EPI>
+// The unit geometry of a band of `band_rows` rows (see UnitGeo); halo_top / halo_bot > 0: the band has a neighbour on that side whose halo is that high
+UnitGeo unit_geometry(int nx, int band_rows, int resident, int rmax, bool hints_on, int halo_top, int halo_bot) {
+	const int R = pick_rows(nx, band_rows, resident, rmax);
+	// the last rows of the band in short units
+	// (measured on B200, 4K pan + one mover, R = 26: no hints, no tail 0.1033 ms; hints alone 0.1043; tail alone 0.1054; hints + 15 % tail in units of 14
+	// rows 0.0958; 25 %: 0.0960; 35 %: 0.0994; units of 8 rows: 0.0968 .. 0.1015)
+	static const int tail_env = [] { const char* v = getenv("TAA_STREAM_TAIL"); return v ? atoi(v) : -1; }();   // tuning aids
+	const int tail_pct = tail_env >= 0 ? tail_env : (hints_on ? 20 : 0);
+	static const int rs_env = [] { const char* v = getenv("TAA_STREAM_RS"); return v ? atoi(v) : 0; }();
+	UnitGeo geo;
+	geo.nx = nx; geo.R = R;
+	geo.Rs = rs_env >= 2 && rs_env <= R ? rs_env : max(2, (R / 2 + 1) & ~1);
+	geo.nbig = tail_pct > 0 ? (int)(((long long)band_rows * (100 - min(tail_pct, 100)) / 100) / R) : (band_rows + R - 1) / R;
+	const int rest = max(0, band_rows - geo.nbig * R);
+	geo.ny = geo.nbig + (rest + geo.Rs - 1) / geo.Rs;
+	geo.nbt = geo.nbb = 0;
+	for (int b = 0; b < geo.ny; ++b) {
+		const int y = b < geo.nbig ? b * R : geo.nbig * R + (b - geo.nbig) * geo.Rs;
+		const int e = min(band_rows, y + (b < geo.nbig ? R : geo.Rs));
+		if (halo_top > 0 && y < halo_top) ++geo.nbt;
+		if (halo_bot > 0 && e > band_rows - halo_bot) ++geo.nbb;
+	}
+	return geo;
+}
+
+template <bool REJ, bool ALPHA, bool DIAG, int FX, int MINB, int EPI, bool PEER = false>
 cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const CUtensorMap& tmV, const CUtensorMap& tmD, unsigned int* fix_list, unsigned int* fix_count,
-                           unsigned int* fix_count_next, float band, int num_sms, unsigned int* hints, int hint_phase, cudaStream_t stream) {
-	auto kern = taa_resolve_stream_kernel<REJ, ALPHA, DIAG, FX, MINB, EPI>;
+                           unsigned int* fix_count_next, float band, int num_sms, unsigned int* hints, int hint_phase, const StreamPeers* peers, cudaStream_t stream) {
+	auto kern = taa_resolve_stream_kernel<REJ, ALPHA, DIAG, FX, MINB, EPI, PEER>;
 	const int smem = (int)sizeof(WarpSmem<REJ>) * NWARP;
 	static int resident_per_sm[64] = {0};  // per device (the attribute and the occupancy are per device)
 	int dev = 0;
@@ -1119,22 +1218,26 @@ cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const C
 	// strips: 62 output columns starting at column -1 (the first strip's first column does not exist), or 60 starting at 0 with an epilogue
 	const int nstrips = EPI ? (A.out_w + OWS - 3) / (OWS - 2) : (A.out_w + 1 + OWS - 1) / OWS;
 	const int nx = (nstrips + NWARP - 1) / NWARP;
-	const int R = pick_rows(nx, A.band_rows, resident_per_sm[dev] * num_sms, EPI ? RMAX - 2 : RMAX);
+	const int resident = resident_per_sm[dev] * num_sms, rmax = EPI ? RMAX - 2 : RMAX;
 	cudaLaunchConfig_t cfg = {};
 	static const bool hints_off = [] { const char* v = getenv("TAA_STREAM_HINTS"); return v && v[0] == '0'; }();  // A/B aid
 	const bool hints_on = hints && !hints_off;
-	// the last rows of the band in short units (see UnitGeo)
-	// (measured on B200, 4K pan + one mover, R = 26: no hints, no tail 0.1033 ms; hints alone 0.1043; tail alone 0.1054; hints + 15 % tail in units of 14
-	// rows 0.0958; 25 %: 0.0960; 35 %: 0.0994; units of 8 rows: 0.0968 .. 0.1015)
-	static const int tail_env = [] { const char* v = getenv("TAA_STREAM_TAIL"); return v ? atoi(v) : -1; }();   // tuning aids
-	const int tail_pct = tail_env >= 0 ? tail_env : (hints_on ? 20 : 0);
-	static const int rs_env = [] { const char* v = getenv("TAA_STREAM_RS"); return v ? atoi(v) : 0; }();
-	UnitGeo geo;
-	geo.nx = nx; geo.R = R;
-	geo.Rs = rs_env >= 2 && rs_env <= R ? rs_env : max(2, (R / 2 + 1) & ~1);
-	geo.nbig = tail_pct > 0 ? (int)(((long long)A.band_rows * (100 - min(tail_pct, 100)) / 100) / R) : (A.band_rows + R - 1) / R;
-	const int rest = max(0, A.band_rows - geo.nbig * R);
-	const int ny = geo.nbig + (rest + geo.Rs - 1) / geo.Rs;
+	const bool up = PEER && peers->nb_hist[0], dn = PEER && peers->nb_hist[1];
+	const UnitGeo geo = unit_geometry(nx, A.band_rows, resident, rmax, hints_on, up ? peers->halo : 0, dn ? peers->halo : 0);
+	const int ny = geo.ny, R = geo.R;
+	PeerArgs pa = {};
+	if (PEER) {
+		if (geo.nbt + geo.nbb > ny || peers->halo > A.band_rows) return cudaErrorInvalidConfiguration;  // (a band lower than its two halos)
+		for (int sd = 0; sd < 2; ++sd) {
+			pa.nb_hist[sd] = peers->nb_hist[sd]; pa.nb_pitch[sd] = peers->nb_pitch[sd]; pa.nb_y0[sd] = peers->nb_y0[sd]; pa.nb_flags[sd] = peers->nb_flags[sd];
+			if (!peers->nb_hist[sd]) continue;
+			// what the neighbour signals: the warps of ITS boundary blocks that face this band (same function of its band height)
+			const UnitGeo ng = unit_geometry(nx, peers->nb_band_rows[sd], resident, rmax, hints_on, peers->halo, peers->halo);
+			pa.expect[sd] = (unsigned int)((sd == 0 ? ng.nbb : ng.nbt) * nstrips);
+			pa.mine[sd] = (unsigned int)((sd == 0 ? geo.nbt : geo.nbb) * nstrips);
+		}
+		pa.flags = peers->flags; pa.halo = peers->halo; pa.q = peers->q; pa.wait = peers->wait;
+	}
 	const bool hinted = hints_on && (long long)nx * ny <= (long long)HINT_FLAGS;
 	const unsigned int* hin = hinted ? hints + (size_t)(hint_phase % 3) * HINT_WORDS : nullptr;
 	unsigned int* hout = hinted ? hints + (size_t)((hint_phase + 1) % 3) * HINT_WORDS : nullptr;
@@ -1149,7 +1252,7 @@ cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const C
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
-	return cudaLaunchKernelEx(&cfg, kern, A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, geo, 0u, hin, hout, hclr, sig);
+	return cudaLaunchKernelEx(&cfg, kern, A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, geo, 0u, hin, hout, hclr, sig, pa);
 }
 
 }  // namespace
@@ -1185,7 +1288,7 @@ bool stream_epilogue_ok(const ResolveArgs& A, bool fixup_all) {
 size_t stream_hint_bytes() { return 3u * (size_t)HINT_WORDS * sizeof(unsigned int); }
 
 cudaError_t launch_resolve_stream(const ResolveArgs& A, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next, bool fixup_all, int num_sms,
-                                  unsigned int* hints, int hint_phase, cudaStream_t stream) {
+                                  unsigned int* hints, int hint_phase, const StreamPeers* peers, cudaStream_t stream) {
 	const float band = fixup_all ? INFINITY : FIXUP_BAND_4K * fmaxf(1.0f, fmaxf((float)A.out_w / 3840.0f, (float)A.out_h / 3840.0f));
 	const TaaParameters& P = A.ubo.param[0];
 	const bool rej = P.mDepthCulling || P.mRejectOutside || P.mDynamicAntiGhosting;
@@ -1199,9 +1302,14 @@ cudaError_t launch_resolve_stream(const ResolveArgs& A, unsigned int* fix_list, 
 	static const int minb_env = [] { const char* v = getenv("TAA_STREAM_MINB"); return v ? atoi(v) : 0; }();
 	const bool fx3 = rej && alp && P.mDepthCulling && P.mRejectOutside && P.mDynamicAntiGhosting && P.mVelBasedAlpha && P.mLumaWeightingLottes &&
 	                 !P.mReduceBlendNearClamp && !A.ubo.mResetHistory;
-#define TAA_STREAM_GO(RJ, AL, DG, FX, MB) return launch_variant<RJ, AL, DG, FX, MB, 0>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, hints, hint_phase, stream)
+#define TAA_STREAM_GO(RJ, AL, DG, FX, MB) return launch_variant<RJ, AL, DG, FX, MB, 0>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, hints, hint_phase, nullptr, stream)
+	if (peers) {  // boundary rows stored into the neighbours' halos, completion by flags: plain variants only (a fix-up pass would rewrite stored pixels)
+		if (rej || diag || A.epilogue) return cudaErrorNotSupported;
+		if (alp) return launch_variant<false, true, false, 0, 6, 0, true>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, hints, hint_phase, peers, stream);
+		return launch_variant<false, false, false, 0, 6, 0, true>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, hints, hint_phase, peers, stream);
+	}
 	if (A.epilogue) {  // (stream_epilogue_ok() has admitted the call: a plain variant, nothing for the exact pass to decide)
-#define TAA_STREAM_EPI(AL, MB, EP) return launch_variant<false, AL, false, 0, MB, EP>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, hints, hint_phase, stream)
+#define TAA_STREAM_EPI(AL, MB, EP) return launch_variant<false, AL, false, 0, MB, EP>(A, tmC, tmV, tmD, fix_list, fix_count, fix_count_next, band, num_sms, hints, hint_phase, nullptr, stream)
 		static const int epi_minb = [] { const char* v = getenv("TAA_STREAM_EPI_MINB"); return v ? atoi(v) : 0; }();  // tuning aid
 		if (A.epilogue == 1) { if (alp) TAA_STREAM_EPI(true, 5, 1); TAA_STREAM_EPI(false, 5, 1); }
 		if (alp) TAA_STREAM_EPI(true, 5, 2);
