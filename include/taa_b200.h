@@ -50,7 +50,8 @@ enum {
 	TAA_E_UNSUPPORTED   = -2,
 	TAA_E_CUDA          = -3,
 	TAA_E_NCCL          = -4,
-	TAA_E_HALO_OVERFLOW = -5   /* a history gather left the rows available to this band */
+	TAA_E_HALO_OVERFLOW = -5,  /* a history gather left the rows available to this band */
+	TAA_E_PEER_TIMEOUT = -6    /* taa_band_peers: a neighbour's boundary rows did not arrive */
 };
 
 /* ---- TAA_RTFLAG_* (shaders/shader_cpu_common.h:31-40) ---- */
@@ -288,6 +289,39 @@ TAA_API int taa_fxaa(taa_ctx* ctx, const taa_image* src_prepared, const taa_imag
 /* both dispatches in one launch: reads the screen result itself, bit-identical to taa_fxaa_prepare + taa_fxaa */
 TAA_API int taa_fxaa_fused(taa_ctx* ctx, const taa_image* src, const taa_image* segmask, const taa_image* dst,
                            const TaaFxaaPush* pc, void* stream);
+
+/*
+ * Row-band sharding without a per-frame collective (new work: the reference is single-GPU, main.cpp:4973; BASELINE configs[3]).
+ * A band context whose neighbours' history buffers are mapped into this process stores the first / last `halo_rows` rows of
+ * history_out a second time, straight into the neighbours' halo rows (peer memory over NVLink), from the resolve kernel itself,
+ * and signals a counter in the neighbour's flag block; the neighbour's boundary units of the NEXT frame wait on that counter
+ * before they read the halo. One launch per band and frame, no send/recv, no host synchronisation between the ranks.
+ *   - every rank allocates its two history buffers and one flag block of TAA_BAND_FLAG_WORDS uint32 (taa_device_alloc),
+ *     exports them (taa_ipc_export), exchanges the handles once (any transport) and opens its neighbours' (taa_ipc_open);
+ *   - taa_band_peers() registers them and zeroes the own flag block: all ranks must have returned from it before any of them
+ *     resolves (one barrier at set-up), and all ranks must write the SAME ping-pong index (history[k]) in the same frame;
+ *   - calls on such a context must be served by the streaming kernel alone (config 2 family without a mask binding and
+ *     without mDynamicAntiGhosting: the exact fix-up pass would rewrite pixels a neighbour already holds) — other calls fail;
+ *   - a neighbour that never signals is reported by taa_poll_status as TAA_E_PEER_TIMEOUT after ~17 s, not as a hang.
+ * up / down may be NULL (first / last band).
+ */
+#define TAA_BAND_FLAG_WORDS 16
+typedef struct taa_band_peer {
+	void*     history[2];  /* the neighbour's history ping-pong buffers as mapped into this process; [k] pairs with own history k */
+	int64_t   row_pitch;
+	int32_t   y0;          /* global row index stored in the neighbour's buffer row 0 */
+	int32_t   band_rows;   /* output rows the neighbour resolves per frame */
+	uint32_t* flags;       /* the neighbour's flag block as mapped into this process */
+} taa_band_peer;
+TAA_API int taa_band_peers(taa_ctx* ctx, const taa_band_peer* up, const taa_band_peer* down, void* own_history0, void* own_history1,
+                           uint32_t* own_flags, int32_t halo_rows);
+/* device memory that can be exported to other processes of the node (plain cudaMalloc: not from a pooled allocator) */
+TAA_API void* taa_device_alloc(size_t bytes);
+TAA_API void  taa_device_free(void* p);
+#define TAA_IPC_HANDLE_BYTES 64
+TAA_API int taa_ipc_export(const void* device_alloc_ptr, void* handle_out /* TAA_IPC_HANDLE_BYTES */);
+TAA_API int taa_ipc_open(const void* handle /* TAA_IPC_HANDLE_BYTES */, void** mapped_out);
+TAA_API int taa_ipc_close(void* mapped);
 
 /* number of CUDA kernels launched through this context so far (bench.py reports it as gpu_launches) */
 TAA_API long long taa_launch_count(const taa_ctx* ctx);

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""torchrun, one rank per GPU: the row-band sharded resolve (taa_star_b200/sharded.py, NCCL halo exchange) against the whole-frame
+"""torchrun, one rank per GPU: the row-band sharded resolve (taa_star_b200/sharded.py; peer stores and NCCL halo exchange) against the whole-frame
 resolve of the same sequence computed redundantly on every rank. Bit-identical history and result rows are required, frame after frame.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/sharded_check.py"""
 import os
@@ -23,11 +23,11 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     W, H, halo = 1920, 1080, 20
     ok = True
-    for cfg_id, replicate in ((2, False), (3, False), (2, True)):
+    for cfg_id, replicate, exchange in ((2, False, "peer"), (2, False, "nccl"), (3, False, "nccl"), (2, True, "nccl")):
         p = configs.config2_resolve() if cfg_id == 2 else configs.config3_full_chain()
-        sh = ShardedTaa(W, H, halo=halo, device=dev, apron=halo if cfg_id == 3 else 2, replicate=replicate)
+        sh = ShardedTaa(W, H, halo=halo, device=dev, apron=halo if cfg_id == 3 else 2, replicate=replicate, exchange=exchange)
         L = sh.L
-        sc = SyntheticScene(W, H, device=dev, with_aux=False, pan_px=(3.0, 7.5), mover_px=(-6.0, 5.0))
+        sc = SyntheticScene(W, H, device=dev, with_aux=False, pan_px=(3.25, 7.5), mover_px=(-6.5, 5.25))  # (not whole texels: see _whole_frame_reference in sharded.py)
         whole = host.TaaContext((W, H))
         hist = [torch.zeros(H, W, 4, dtype=torch.float16, device=dev) for _ in range(2)]
         res = torch.zeros(H, W, 4, dtype=torch.float16, device=dev)
@@ -42,9 +42,12 @@ def main():
             a1 = L.iy1 if cfg_id == 2 else min(H, L.y1 + halo)
             sh.step(u, f.color[a0:a1].contiguous(), f.depth[a0:a1].contiguous(), f.velocity[a0:a1].contiguous(), a0,
                     history_depth=hd[a0:a1].contiguous() if cfg_id == 3 else None)
+            if exchange == "peer" and n % 3 != 2:
+                prev_depth = f.depth
+                continue  # (no host synchronisation between the ranks' frames: the flags alone order the halo stores and reads)
             torch.cuda.synchronize()
             dist.barrier()
-            assert sh.poll() == abi.TAA_OK, "halo overflow"
+            assert sh.poll() == abi.TAA_OK, "halo overflow / peer time-out"
             got_hist = sh.hist[sh.parity]  # the buffer just written (parity already flipped)
             ref_hist = hist[1 - (n & 1)]
             lo, hi = (0, H) if replicate else (L.hy0, L.hy1)
@@ -52,14 +55,15 @@ def main():
             same_r = torch.equal(sh.result.view(torch.int16), res.view(torch.int16)[L.y0:L.y1])
             if not (same_h and same_r):
                 ok = False
-                print(f"rank {rank} cfg {cfg_id} replicate {replicate} frame {n}: history rows equal {same_h}, result rows equal {same_r}", flush=True)
+                print(f"rank {rank} cfg {cfg_id} replicate {replicate} exchange {exchange} frame {n}: history rows equal {same_h}, result rows equal {same_r}", flush=True)
                 break
             prev_depth = f.depth
+        sh.close()
         del sh, whole
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     if rank == 0:
-        print("sharded_check:", "OK" if flag.item() == 0 else "FAILED", f"({world} ranks, {W}x{H}, halo {halo}, configs 2/3 + replicated history, 12 frames each)", flush=True)
+        print("sharded_check:", "OK" if flag.item() == 0 else "FAILED", f"({world} ranks, {W}x{H}, halo {halo}, config 2 with peer stores, configs 2/3 over NCCL, replicated history; 12 frames each)", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 0 else 1)
 

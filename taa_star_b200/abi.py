@@ -11,7 +11,8 @@ import os
 
 ABI_VERSION = 2
 
-TAA_OK, TAA_E_INVALID_ARG, TAA_E_UNSUPPORTED, TAA_E_CUDA, TAA_E_NCCL, TAA_E_HALO_OVERFLOW = 0, -1, -2, -3, -4, -5
+TAA_OK, TAA_E_INVALID_ARG, TAA_E_UNSUPPORTED, TAA_E_CUDA, TAA_E_NCCL, TAA_E_HALO_OVERFLOW, TAA_E_PEER_TIMEOUT = 0, -1, -2, -3, -4, -5, -6
+TAA_BAND_FLAG_WORDS, TAA_IPC_HANDLE_BYTES = 16, 64
 TAA_FLAG_DEFAULT, TAA_FLAG_EXACT, TAA_FLAG_FIXUP_ALL = 0, 1, 2
 
 # shaders/shader_cpu_common.h:31-40
@@ -89,6 +90,11 @@ class taa_desc(C.Structure):
                 ("out_height", _i32), ("band_y0", _i32), ("band_rows", _i32), ("device", _i32), ("flags", _u32)]
 
 
+class taa_band_peer(C.Structure):
+    """A neighbour band as mapped into this process (taa_band_peers)."""
+    _fields_ = [("history", C.c_void_p * 2), ("row_pitch", C.c_int64), ("y0", _i32), ("band_rows", _i32), ("flags", C.c_void_p)]
+
+
 class taa_jitter_settings(C.Structure):
     _fields_ = [("mSampleDistribution", _i32), ("mFixedJitterIndex", _i32), ("mJitterExtraScale", _f32), ("mJitterSlowMotion", _i32),
                 ("mJitterRotateDegrees", _f32), ("mDebugSampleOffsets", C.POINTER(_f32)), ("mDebugSampleOffsetsCount", _i32)]
@@ -160,6 +166,12 @@ SIGNATURES = {
     "taa_settings_ini_last_error": (C.c_char_p, []),
     "taa_invokee_write_settings_ini": (C.c_int32, [_vp, C.c_char_p, C.c_int32]),
     "taa_invokee_read_settings_ini": (C.c_int, [_vp, C.c_char_p]),
+    "taa_band_peers": (C.c_int, [_vp, _P(taa_band_peer), _P(taa_band_peer), _vp, _vp, _vp, _i32]),
+    "taa_device_alloc": (_vp, [C.c_size_t]),
+    "taa_device_free": (None, [_vp]),
+    "taa_ipc_export": (C.c_int, [_vp, _vp]),
+    "taa_ipc_open": (C.c_int, [_vp, _P(_vp)]),
+    "taa_ipc_close": (C.c_int, [_vp]),
     "taa_host_alloc": (_vp, [C.c_size_t]),
     "taa_host_free": (None, [_vp]),
 }

@@ -146,6 +146,7 @@ const char* taa_status_string(int s) {
 		case TAA_E_CUDA: return "TAA_E_CUDA";
 		case TAA_E_NCCL: return "TAA_E_NCCL";
 		case TAA_E_HALO_OVERFLOW: return "TAA_E_HALO_OVERFLOW";
+		case TAA_E_PEER_TIMEOUT: return "TAA_E_PEER_TIMEOUT";
 		default: return "TAA_E_UNKNOWN";
 	}
 }
@@ -405,8 +406,76 @@ int taa_poll_status(taa_ctx* c, void* stream) {
 	if (e == cudaSuccess) e = cudaMemsetAsync(c->d_status, 0, sizeof h, (cudaStream_t)stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
 	if (e != cudaSuccess) return cuda_fail(c, e, "taa_poll_status");
-	if (h & 1u) { set_error(c, "a gather left the rows held by a band buffer (halo too small for this motion)"); return TAA_E_HALO_OVERFLOW; }
+	if (h & 1u) {
+		set_error(c, "a read left the rows held by a band buffer (status word 0x%x: 0x10 colour, 0x20 velocity, 0x40 depth apron too small; none of them: history halo too small for this motion)", h);
+		return TAA_E_HALO_OVERFLOW;
+	}
+	if (h & 2u) { set_error(c, "a neighbour band's boundary rows did not arrive (taa_band_peers)"); return TAA_E_PEER_TIMEOUT; }
 	return TAA_OK;
+}
+
+// ---- row bands without a per-frame collective (see include/taa_b200.h and "PEER variants" in taa_resolve_stream.cu) ----
+int taa_band_peers(taa_ctx* c, const taa_band_peer* up, const taa_band_peer* down, void* own_history0, void* own_history1, uint32_t* own_flags, int32_t halo_rows) {
+	if (!c) return TAA_E_INVALID_ARG;
+	if (!up && !down) { c->peers.on = false; return TAA_OK; }
+	if (!own_history0 || !own_history1 || own_history0 == own_history1 || !own_flags || halo_rows <= 0 || halo_rows > c->desc.band_rows) {
+		set_error(c, "taa_band_peers: two distinct own history buffers, a flag block and 0 < halo_rows <= band_rows are required");
+		return TAA_E_INVALID_ARG;
+	}
+	const taa_band_peer* in[2] = {up, down};
+	for (int sd = 0; sd < 2; ++sd) {
+		c->peers.has[sd] = in[sd] != nullptr;
+		if (!in[sd]) continue;
+		const taa_band_peer& n = *in[sd];
+		if (!n.history[0] || !n.history[1] || !n.flags || n.band_rows < halo_rows || n.row_pitch < (int64_t)c->desc.out_width * 8 ||
+		    (((uintptr_t)n.history[0] | (uintptr_t)n.history[1] | (uintptr_t)n.row_pitch) & 15u)) {
+			set_error(c, "taa_band_peers: neighbour %d needs two mapped history buffers (16-byte aligned base and pitch), a mapped flag block and band_rows >= halo_rows", sd);
+			return TAA_E_INVALID_ARG;
+		}
+		c->peers.side[sd] = n;
+	}
+	int cur = -1;
+	if (cudaGetDevice(&cur) == cudaSuccess && cur != c->desc.device) cudaSetDevice(c->desc.device);
+	cudaError_t e = cudaMemset(own_flags, 0, TAA_BAND_FLAG_WORDS * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaDeviceSynchronize();
+	if (e != cudaSuccess) return cuda_fail(c, e, "taa_band_peers");
+	c->peers.own_hist[0] = own_history0;
+	c->peers.own_hist[1] = own_history1;
+	c->peers.flags = own_flags;
+	c->peers.halo = halo_rows;
+	c->peers.first = true;
+	c->peers.on = true;
+	return TAA_OK;
+}
+
+void* taa_device_alloc(size_t bytes) {
+	void* p = nullptr;
+	if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	cudaMemset(p, 0, bytes);
+	return p;
+}
+void taa_device_free(void* p) { if (p) cudaFree(p); }
+static_assert(sizeof(cudaIpcMemHandle_t) == TAA_IPC_HANDLE_BYTES, "IPC handle size");
+int taa_ipc_export(const void* p, void* handle_out) {
+	if (!p || !handle_out) return TAA_E_INVALID_ARG;
+	cudaIpcMemHandle_t h;
+	cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(p));
+	if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaIpcGetMemHandle");
+	memcpy(handle_out, &h, sizeof h);
+	return TAA_OK;
+}
+int taa_ipc_open(const void* handle, void** mapped_out) {
+	if (!handle || !mapped_out) return TAA_E_INVALID_ARG;
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof h);
+	cudaError_t e = cudaIpcOpenMemHandle(mapped_out, h, cudaIpcMemLazyEnablePeerAccess);
+	if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaIpcOpenMemHandle");
+	return TAA_OK;
+}
+int taa_ipc_close(void* mapped) {
+	if (!mapped) return TAA_OK;
+	cudaError_t e = cudaIpcCloseMemHandle(mapped);
+	return e == cudaSuccess ? TAA_OK : cuda_fail(nullptr, e, "cudaIpcCloseMemHandle");
 }
 
 long long taa_launch_count(const taa_ctx* c) { return c ? c->launches : 0; }

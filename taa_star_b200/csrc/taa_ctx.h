@@ -15,6 +15,15 @@ struct taa_ctx {
 	int fix_parity = 0;
 	unsigned int* hints = nullptr;     // streaming kernel: units that were slow in the previous call (three rotating buffers)
 	int hint_phase = 0;
+	// row-band sharding without a per-frame collective (taa_band_peers): side 0 = the band above, 1 = the band below
+	struct {
+		bool on = false, first = true;
+		void* own_hist[2] = {nullptr, nullptr};
+		taa_band_peer side[2] = {};
+		bool has[2] = {false, false};
+		uint32_t* flags = nullptr;
+		int halo = 0;
+	} peers;
 	bool last_was_tuned = false;
 	long long launches = 0;            // kernels launched through this context
 	std::string last_error;

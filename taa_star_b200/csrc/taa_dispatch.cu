@@ -40,8 +40,26 @@ cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, i
 			if (cudaMalloc(&c->hints, stream_hint_bytes()) == cudaSuccess) cudaMemsetAsync(c->hints, 0, stream_hint_bytes(), s);
 			else { c->hints = nullptr; cudaGetLastError(); }
 		}
+		StreamPeers sp, *peers = nullptr;
+		if (c->peers.on) {
+			// the boundary rows are stored into the neighbours' buffers by the resolve kernel itself: only a call that the streaming kernel serves alone
+			// can do that (an exact fix-up pass would rewrite pixels the neighbour already holds)
+			const int q = A.history_out.p == c->peers.own_hist[0] ? 0 : A.history_out.p == c->peers.own_hist[1] ? 1 : -1;
+			if (!streaming || need_fixup || q < 0) {
+				set_error(c, "taa_band_peers is set: the call must run on the streaming kernel alone (config 2 family, no mask, no dynamic anti-ghosting) and write one of the two registered history buffers");
+				return cudaErrorNotSupported;
+			}
+			for (int sd = 0; sd < 2; ++sd) {
+				const taa_band_peer& n = c->peers.side[sd];
+				sp.nb_hist[sd] = c->peers.has[sd] ? (unsigned char*)n.history[q] : nullptr;
+				sp.nb_pitch[sd] = n.row_pitch; sp.nb_y0[sd] = n.y0; sp.nb_band_rows[sd] = n.band_rows; sp.nb_flags[sd] = n.flags;
+			}
+			sp.flags = c->peers.flags; sp.halo = c->peers.halo; sp.q = q; sp.wait = c->peers.first ? 0 : 1;
+			c->peers.first = false;
+			peers = &sp;
+		}
 		cudaError_t e = tile ? launch_resolve_tuned(A, list, cnt, cnt_next, fixup_all, s)
-		                     : streaming ? launch_resolve_stream(A, list, cnt, cnt_next, fixup_all, c->num_sms, c->hints, c->hint_phase++, s)
+		                     : streaming ? launch_resolve_stream(A, list, cnt, cnt_next, fixup_all, c->num_sms, c->hints, c->hint_phase++, peers, s)
 		                                 : launch_resolve_strip(A, list, cnt, cnt_next, fixup_all, s);
 		if (c->hint_phase >= 3 * 1024) c->hint_phase -= 3 * 1024;
 		if (e != cudaSuccess) return e;

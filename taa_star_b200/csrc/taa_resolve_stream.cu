@@ -137,10 +137,10 @@ __device__ __forceinline__ AxisW catmull_axis_k(float h, float size, float inv, 
 }
 
 // global row gy as a row the buffer holds (clamped into it; reported when the row was really asked for)
-__device__ __forceinline__ int buf_row(const Img& im, int gy, unsigned int* st, bool used) {
+__device__ __forceinline__ int buf_row(const Img& im, int gy, unsigned int* st, bool used, unsigned int which = 0u) {
 	int ly = gy - im.y0;
 	if ((unsigned int)ly >= (unsigned int)im.rows) {
-		if (st && used) atomicOr(st, 1u);
+		if (st && used) atomicOr(st, 1u | which);  // (bits 4 .. 6 say which input it was: diagnostics)
 		ly = ly < 0 ? 0 : im.rows - 1;
 	}
 	return ly + im.y0;
@@ -465,7 +465,7 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 				const unsigned int* f = peer.flags + (2 * sd + (peer.q ^ 1));
 				while (ld_acquire_sys(f) < peer.expect[sd]) {
 					__nanosleep(64);
-					if (clock64() - t0 > (1ll << 32)) { if (st) atomicOr(st, 2u); break; }  // (~2 s: reported as a peer time-out, never a hang)
+					if (clock64() - t0 > (1ll << 35)) { if (st) atomicOr(st, 2u); break; }  // (~17 s: reported as a peer time-out, never a hang)
 				}
 			}
 		}
@@ -545,15 +545,15 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 		float p;
 		colour_axis(g, invh, H, m, n, p);
 		const bool cused = lane <= nr + 1;  // sampled rows Y0 - 1 .. Y0 + nr
-		const unsigned int cm = ring_row(buf_row(A.color, m, st, cused), Y0 - 2, NR) * ROWB, cn = ring_row(buf_row(A.color, n, st, cused), Y0 - 2, NR) * ROWB;
+		const unsigned int cm = ring_row(buf_row(A.color, m, st, cused, 16u), Y0 - 2, NR) * ROWB, cn = ring_row(buf_row(A.color, n, st, cused, 16u), Y0 - 2, NR) * ROWB;
 		const __half ph = __float2half_rn(p);
 		sm.tabC[lane] = make_uint4(cm | (cn << 16), (unsigned int)__half_as_ushort(ph), 0u, 0u);
 		const float v = ((float)g + 0.5f) / fH;
 		const Lin L = lin_coord(v, H);
 		const bool vused = lane >= 1 && lane <= nr;  // output rows
-		const unsigned int o0 = ring_row(buf_row(A.velocity, L.i0, st, vused), Y0 - 3, NR) * ROWB, o1 = ring_row(buf_row(A.velocity, L.i1, st, vused), Y0 - 3, NR) * ROWB;
+		const unsigned int o0 = ring_row(buf_row(A.velocity, L.i0, st, vused, 32u), Y0 - 3, NR) * ROWB, o1 = ring_row(buf_row(A.velocity, L.i1, st, vused, 32u), Y0 - 3, NR) * ROWB;
 		sm.tabB[lane] = make_uint4(o0 | (o1 << 16), __float_as_uint(L.a), __float_as_uint(v), 0u);
-		if (use_depth && vused) buf_row(A.depth, g, st, true);
+		if (use_depth && vused) buf_row(A.depth, g, st, true, 64u);
 	}
 	__syncwarp();
 

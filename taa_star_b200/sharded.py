@@ -91,17 +91,26 @@ def gather_full_history(band: torch.Tensor, full: torch.Tensor, layout: BandLayo
 class ShardedTaa:
     """One rank's share of a row-band sharded resolve. Inputs for the band (plus apron) are produced locally."""
 
-    def __init__(self, width: int, height: int, halo: int = 20, replicate: bool = False, flags: int = 0, device=None, group=None, apron: int = 2):
+    def __init__(self, width: int, height: int, halo: int = 20, replicate: bool = False, flags: int = 0, device=None, group=None, apron: int = 2,
+                 exchange: str = "nccl"):
+        """exchange = "nccl": the boundary strips are resolved by their own launches and sent / received (works for every settings block);
+        "peer": ONE launch per band and frame, the resolve kernel stores the boundary rows into the neighbours' halos itself and the next frame's
+        boundary units wait on a flag (taa_band_peers; calls the streaming kernel serves alone, i.e. the config 2 family)."""
         from . import host
+        assert exchange in ("nccl", "peer")
         self.W, self.H = width, height
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.L = BandLayout(height, self.world, self.rank, halo, apron)
         self.replicate = replicate
         self.group = group
         self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.peer = exchange == "peer" and self.world > 1 and not replicate
         L = self.L
         rows = (height if replicate else L.hy1 - L.hy0)
         self.hist_y0 = 0 if replicate else L.hy0
+        if self.peer:
+            self._peer_setup(rows, flags)
+            return
         self.hist = [torch.zeros(rows, width, 4, dtype=torch.float16, device=self.device) for _ in range(2)]
         self.result = torch.zeros(L.rows, width, 4, dtype=torch.float16, device=self.device)
         self.band_tmp = torch.zeros(L.rows, width, 4, dtype=torch.float16, device=self.device) if replicate else None
@@ -131,12 +140,97 @@ class ShardedTaa:
         self._ev_comm_captured = False
         self._comm_in_capture = False
 
+    # ---- exchange = "peer" ---------------------------------------------------------------------------------------------------------
+    def _peer_setup(self, rows: int, flags: int):
+        """One exportable allocation per rank: [history 0 | history 1 | flag block]; the handles travel once through torch.distributed."""
+        import ctypes as C
+        from . import abi, host
+        L, W = self.L, self.W
+        lib = abi.load_library()
+        self._lib = lib
+        hbytes = rows * W * 8
+        self._arena = lib.taa_device_alloc(2 * hbytes + 4 * abi.TAA_BAND_FLAG_WORDS)
+        assert self._arena, "taa_device_alloc failed"
+        self.hist = [host.tensor_from_ptr(self._arena + k * hbytes, (rows, W, 4), torch.float16) for k in range(2)]
+        self._flags_ptr = self._arena + 2 * hbytes
+        handle = (C.c_ubyte * abi.TAA_IPC_HANDLE_BYTES)()
+        st = lib.taa_ipc_export(self._arena, handle)
+        assert st == abi.TAA_OK, "taa_ipc_export failed"
+        mine = dict(handle=bytes(handle), hbytes=hbytes, hy0=L.hy0, band_rows=L.rows)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        self._mapped = []
+        peers = [None, None]
+        for sd, nb in enumerate((self.rank - 1, self.rank + 1)):
+            if nb < 0 or nb >= self.world:
+                continue
+            info = everyone[nb]
+            base = C.c_void_p()
+            st = lib.taa_ipc_open((C.c_ubyte * abi.TAA_IPC_HANDLE_BYTES).from_buffer_copy(info["handle"]), C.byref(base))
+            assert st == abi.TAA_OK, f"taa_ipc_open failed: {lib.taa_last_error_string(None).decode()}"
+            self._mapped.append(base.value)
+            pb = abi.taa_band_peer()
+            pb.history[0], pb.history[1] = base.value, base.value + info["hbytes"]
+            pb.row_pitch, pb.y0, pb.band_rows = W * 8, info["hy0"], info["band_rows"]
+            pb.flags = base.value + 2 * info["hbytes"]
+            peers[sd] = pb
+        self._peers = peers
+        self.result = torch.zeros(L.rows, W, 4, dtype=torch.float16, device=self.device)
+        self.band_tmp = None
+        self.boundary, self.s_boundary, self.ev_boundary = [], [], []
+        self.interior = host.TaaContext((W, self.H), band=(L.y0, L.rows), flags=flags)
+        self.compute = torch.cuda.Stream(device=self.device)
+        self.comm = self.compute
+        self.ev_comm = torch.cuda.Event()
+        self.parity = 0
+        self._pending = []
+        self._capturing = self._ev_comm_captured = self._comm_in_capture = False
+        self.peer_reset()
+
+    def peer_reset(self):
+        """(Re)starts a frame sequence: flag blocks zeroed, the next step waits for nobody. Collective (a barrier on each side)."""
+        import ctypes as C
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # nobody is still signalling into a block that is about to be zeroed
+        up, dn = self._peers
+        st = self._lib.taa_band_peers(self.interior._h, C.byref(up) if up is not None else None, C.byref(dn) if dn is not None else None,
+                                      self.hist[0].data_ptr(), self.hist[1].data_ptr(), self._flags_ptr, self.L.halo)
+        self.interior._check(st, "taa_band_peers")
+        self.parity = 0
+        dist.barrier(group=self.group)
+
+    def _peer_step(self, uniforms, color, depth, velocity, in_y0, history_depth=None):
+        L = self.L
+        hin, hout = self.hist[self.parity], self.hist[1 - self.parity]
+        kw = dict(color=(color, in_y0), depth=(depth, in_y0), velocity=(velocity, in_y0), history_in=(hin, self.hist_y0),
+                  history_out=(hout, self.hist_y0), result=(self.result, L.y0))
+        if history_depth is not None:
+            kw["history_depth"] = (history_depth, in_y0)
+        with torch.cuda.stream(self.compute):
+            self.interior.resolve(uniforms, stream=self.compute, **kw)
+        self.parity ^= 1
+
+    def close(self):
+        if self.peer and getattr(self, "_arena", None):
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            self.hist = []
+            for m in self._mapped:
+                self._lib.taa_ipc_close(m)
+            self.interior.close()
+            self._lib.taa_device_free(self._arena)
+            self._arena = None
+
     @property
     def launch_count(self):
         return sum(c.launch_count for c in self.boundary) + (self.interior.launch_count if self.interior else 0)
 
     def step(self, uniforms, color, depth, velocity, in_y0: int, history_depth=None):
         """Resolves this rank's band for one frame. color/depth/velocity hold input rows starting at global row in_y0."""
+        if not self._capturing:  # inputs are usually produced on the caller's current stream: order them before this step's launches
+            self.compute.wait_stream(torch.cuda.current_stream(self.device))
+        if self.peer:
+            return self._peer_step(uniforms, color, depth, velocity, in_y0, history_depth)
         L = self.L
         hin, hout = self.hist[self.parity], self.hist[1 - self.parity]
         kw = dict(color=(color, in_y0), depth=(depth, in_y0), velocity=(velocity, in_y0), history_in=(hin, self.hist_y0),
@@ -219,8 +313,12 @@ class ShardedTaa:
 
     def poll(self) -> int:
         st = 0
+        self.last_poll_error = ""
         for c in self.boundary + ([self.interior] if self.interior else []):
-            st = min(st, c.poll_status(self.compute))
+            s1 = c.poll_status(self.compute)
+            if s1 != 0:
+                self.last_poll_error = c._lib.taa_last_error_string(c._h).decode()
+            st = min(st, s1)
         return st
 
 
@@ -246,12 +344,26 @@ def _whole_frame_reference(W, H, p, flags, dev, cfg_id, sh, halo, replicate):
     torch.cuda.synchronize()
     want_hist, want_res = hist[0][L.y0:L.y1].clone(), res[L.y0:L.y1].clone()
     # the sharded pipeline on the same two frames (band rows + apron of the same inputs)
+    dist.barrier()  # (the ranks reach this point seconds apart; a peer-store step waits for its neighbours on the device)
     for i in range(2):
         sh.step(u[i], f[i].color[L.iy0:L.iy1], f[i].depth[L.iy0:L.iy1], f[i].velocity[L.iy0:L.iy1], L.iy0,
                 history_depth=f[i - 1].depth[L.iy0:L.iy1] if cfg_id == 3 else None)
     torch.cuda.synchronize()
+    st = sh.poll()
+    assert st == 0, f"status {st} in the sharded steps of the whole-frame check: {sh.last_poll_error}"
     got_hist = sh.hist[sh.parity][L.y0 - sh.hist_y0: L.y1 - sh.hist_y0]
-    same = bool(torch.equal(got_hist.view(torch.int16), want_hist.view(torch.int16)) and torch.equal(sh.result.view(torch.int16), want_res.view(torch.int16)))
+    # Exact kernel: bit for bit. Tuned kernels: bit for bit too wherever the motion is not EXACTLY a whole number of texels; where it is (this
+    # scene's 3.0 px pan and its mover), the Catmull-Rom footprint start sits on a rounding tie, the uniform-motion rows break the tie once per
+    # unit, and the unit boundaries of a band differ from the whole frame's: a few hundred pixels of an 8K frame then differ in the last fp16 bit.
+    # The bar is the parity bar of the tuned path (2^-10 per channel); the count of differing pixels is reported.
+    dh = (got_hist.view(torch.int16) != want_hist.view(torch.int16)).any(dim=2)
+    dr = (sh.result.view(torch.int16) != want_res.view(torch.int16)).any(dim=2)
+    ndiff = int(dh.sum()) + int(dr.sum())
+    maxd = max(float((got_hist.float() - want_hist.float()).abs().max()), float((sh.result.float() - want_res.float()).abs().max()))
+    same = (ndiff == 0) if (flags & 1) else (maxd <= 2.0 ** -10)
+    if ndiff:
+        rows_h = torch.nonzero(dh.any(dim=1)).flatten()
+        print(f"[whole-frame check] rank {L.rank}: {ndiff} texels differ from the whole-frame run, max |d| = {maxd:.3g} (band rows {rows_h[:4].tolist()} ..)", flush=True)
     # time the whole frame on one GPU (history ping-pong over the two frames; 2 x 20 B/px of inputs exceed the L2 from 4K upwards)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for k in range(4):
@@ -272,8 +384,10 @@ def _whole_frame_reference(W, H, p, flags, dev, cfg_id, sh, halo, replicate):
         h.zero_()
     if sh.parity:
         sh.parity = 0
+    if sh.peer:
+        sh.peer_reset()
     dist.barrier()
-    return ms, same
+    return ms, same, ndiff, maxd
 
 
 # ---- bench (N > 1) ------------------------------------------------------------------------------------------------------------------
@@ -294,14 +408,17 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
     replicate = bool(getattr(args, "replicate", False))
     if W > 7680:
         halo = halo * W // 7680  # (the synthetic motion and the fix-up band scale with the frame: same angular motion, more pixels)
-    sh = ShardedTaa(W, H, halo=halo, replicate=replicate, flags=flags, device=dev, apron=halo if cfg_id == 3 else 2)
+    # config 2 (the streaming kernel alone): boundary rows stored into the neighbours' halos by the kernel, one launch per band and frame;
+    # config 3 / the exact kernel (a fix-up or general launch rewrites pixels): boundary strips + NCCL send/recv. TAA_SHARDED_EXCHANGE overrides.
+    exchange = os.environ.get("TAA_SHARDED_EXCHANGE", "peer" if (cfg_id == 2 and not args.exact and not replicate) else "nccl")
+    sh = ShardedTaa(W, H, halo=halo, replicate=replicate, flags=flags, device=dev, apron=halo if cfg_id == 3 else 2, exchange=exchange)
     L = sh.L
     NSETS = 4
     # ---- before anything is timed: the same two frames on ONE GPU (every rank does it for itself), (a) as the strong-scaling reference
     # of this very frame size, (b) to check that this rank's band of the sharded result equals the whole-frame result bit for bit ----
-    single_ms, same = None, None
+    single_ms, same, ndiff, maxd = None, None, None, None
     if not getattr(args, "no_verify", False):
-        single_ms, same = _whole_frame_reference(W, H, p, flags, dev, cfg_id, sh, halo, replicate)
+        single_ms, same, ndiff, maxd = _whole_frame_reference(W, H, p, flags, dev, cfg_id, sh, halo, replicate)
     sc = SyntheticScene(W, H, device=dev, with_aux=False, rows=(L.iy0, L.iy1))
     frames = [sc.frame(n) for n in range(NSETS)]
     unis = [configs.uniforms_for(p, f.jitter_ndc) for f in frames]
@@ -312,12 +429,19 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
         sh.step(u or unis[i % NSETS], f.color, f.depth, f.velocity, L.iy0, history_depth=fp.depth if cfg_id == 3 else None)
 
     step(0, u0)
+    if os.environ.get("TAA_SHARDED_DEBUG"):
+        torch.cuda.synchronize()
+        print(f"[debug] rank {rank} step 0: status {sh.poll()} {sh.last_poll_error}; velocity finite {[bool(torch.isfinite(f.velocity.float()).all()) for f in frames]}", flush=True)
     nwarm = max(args.warmup, 1)
     nwarm += (2 * NSETS - (nwarm + 1) % (2 * NSETS)) % (2 * NSETS)  # the next step index is a multiple of the cycle (frame set x history parity)
     for i in range(1, nwarm + 1):
         step(i)
+        if os.environ.get("TAA_SHARDED_DEBUG"):
+            torch.cuda.synchronize()
+            print(f"[debug] rank {rank} warm-up step {i}: status {sh.poll()} {sh.last_poll_error}", flush=True)
     torch.cuda.synchronize()
-    assert sh.poll() == abi.TAA_OK, "halo overflow during warm-up"
+    st = sh.poll()
+    assert st == abi.TAA_OK, f"status {st} during warm-up: {sh.last_poll_error}"
     graphs, cycle_graph, graph_note = None, None, "eager"
     if os.environ.get("TAA_SHARDED_GRAPHS", "1") != "0":
         # One CUDA graph per step of the cycle (kernels + NCCL exchange, see capture_steps) and the whole cycle as one graph (no launch gap
@@ -341,7 +465,8 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 1:
             graphs, cycle_graph = gs, cg
-            graph_note = "CUDA graphs (kernels on 3 streams + the NCCL exchange): one per cycle of 8 steps, single-step graphs for the remainder"
+            graph_note = ("CUDA graphs (one resolve launch per step): one per cycle of 8 steps, single-step graphs for the remainder" if sh.peer else
+                          "CUDA graphs (kernels on 3 streams + the NCCL exchange): one per cycle of 8 steps, single-step graphs for the remainder")
             with torch.cuda.stream(sh.compute):
                 for g in graphs:
                     g.replay()  # run them once: the device state follows the host-side parities the captures advanced
@@ -433,7 +558,12 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
         ok = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         same = bool(ok.item())
-        assert same, "a band of the sharded result differs from the whole-frame result"
+        nd = torch.tensor([float(ndiff), maxd], device=dev)
+        nds = nd.clone()
+        dist.all_reduce(nds, op=dist.ReduceOp.SUM)
+        dist.all_reduce(nd, op=dist.ReduceOp.MAX)
+        ndiff, maxd = int(nds[0].item()), float(nd[1].item())
+        assert same, "a band of the sharded result differs from the whole-frame result by more than the parity bar"
     lps = float(launches.item()) / max(args.steps, 1) / world  # launches per step and rank
     if rank == 0:
         line = {
@@ -444,13 +574,16 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
                        "arithmetic": "exact general kernel" if args.exact else ("tuned kernels + exact fix-up pass" if cfg_id == 3 else "tuned kernels alone (no mask bound: nothing for the exact fix-up pass to decide)"),
                        "halo_rows": halo,
                        "exchange": ("all-gather of the history bands (replicated history: correct for unbounded motion)" if replicate else
+                                    "peer stores: the resolve kernel writes its first / last halo rows into the neighbours' halos over NVLink and signals a flag; "
+                                    "the neighbours' boundary units of the next frame wait on it (taa_band_peers) - one launch per band and frame, no collective" if sh.peer else
                                     "NCCL send/recv of 2 x halo rows of history per neighbour per frame, overlapped with the interior resolve"),
                        "launch": graph_note,
                        "l2": f"inputs larger than L2: {NSETS} frame sets rotated, history ping-pong"},
             "gpu_launches": int(launches.item()), "gpu_launches_per_step_and_rank": round(lps, 2),
             "single_gpu_same_frame_ms": round(single_ms, 5) if single_ms is not None else None,
             "strong_scaling_efficiency_vs_same_frame": round(single_ms / ms_per_step / world, 4) if single_ms is not None else None,
-            "sharded_equals_whole_frame_bit_for_bit": same,
+            "sharded_vs_whole_frame": None if same is None else {"within_parity_bar": same, "differing_texels": ndiff, "max_abs_diff": maxd,
+                                                                  "note": "bit for bit unless the motion is exactly a whole number of texels (rounding tie of the footprint start, broken per unit)"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                          "peak_source": peak_src, "bytes_per_px": BYTES_PER_PX[cfg_id], "kernel": "taa_resolve (per GPU, whole sharded step incl. exchange)"},
             "cpu_baseline": None,
