@@ -295,6 +295,11 @@ def run_single(args):
                                             note="taa_frame: config 3 resolve (strip kernel; the exact pass decides the anti-ghosting predicate) + CAS + post-process in one follow-on launch")
         ms_r, l_r, _ = timed(p3, vel_pan, side_steps, args.warmup, with_hist_depth=True)
         extra["config3_resolve_only"] = block(ms_r, l_r / side_steps, 48)
+        # BASELINE configs[0]: the reference's default settings (RGB min / max clamp, bilinear history, velocity for movers only + matrix
+        # reprojection) on the exact arithmetic: the specialised exact kernel (bit-identical to the oracle), not a tuned one
+        ms_d, l_d, _ = timed(configs.config1_defaults(), vel_pan, side_steps, args.warmup)
+        extra["config1_defaults"] = block(ms_d, l_d / side_steps, 44, note="the reference's default settings on taa_resolve_defaults_kernel: exact arithmetic (all outputs "
+                                          "bit-identical to the oracle), colour taps shared through a shared-memory tile, default switches folded at compile time")
         # the north-star target: fused TAA resolve + CAS — config 2 settings, CAS 0.5 + identity post-process in the resolve's epilogue
         ms_f, l_f, _ = timed(p, vel_pan, side_steps, args.warmup, chain=ch, bind_result=False)
         extra["fused_resolve_cas"] = block(ms_f, l_f / side_steps, 36, note="taa_frame: config 2 settings + CAS 0.5 + post-process, ONE launch (sharpening in the resolve's epilogue); "

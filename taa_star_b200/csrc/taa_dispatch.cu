@@ -71,7 +71,7 @@ cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, i
 		return e;
 	}
 	c->last_was_tuned = false;
-	cudaError_t e = launch_resolve_generic(A, s);
+	cudaError_t e = launch_resolve_generic(A, !(c->desc.flags & TAA_FLAG_EXACT), s);
 	if (e == cudaSuccess) *launched = 1;
 	return e;
 }

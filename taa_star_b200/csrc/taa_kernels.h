@@ -6,7 +6,10 @@
 namespace taa {
 
 // taa.comp, fully general, exact arithmetic (taa_resolve_generic.cu)
-cudaError_t launch_resolve_generic(const ResolveArgs& args, cudaStream_t stream);
+// allow_specialised: a call whose switches are the reference's default pattern (BASELINE configs[0]) may run on taa_resolve_defaults_kernel —
+// the same arithmetic with those switches folded at compile time and the colour taps shared through a shared-memory tile (bit-identical)
+cudaError_t launch_resolve_generic(const ResolveArgs& args, bool allow_specialised, cudaStream_t stream);
+bool defaults_kernel_supports(const ResolveArgs& args);
 // the same exact arithmetic on a device-side list of pixels (y * out_w + x), count read on the device
 cudaError_t launch_resolve_fixup(const ResolveArgs& args, const unsigned int* list, const unsigned int* count, bool write_screen, int num_sms,
                                  cudaStream_t stream);

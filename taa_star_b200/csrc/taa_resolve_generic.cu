@@ -4,6 +4,7 @@
 // taa_resolve_tuned.cu cover the BASELINE configs. Compiled with --fmad=false (see taa_device.cuh).
 #include "taa_device.cuh"
 #include "taa_kernels.h"
+#include <cstdlib>
 
 namespace taa {
 
@@ -185,11 +186,42 @@ struct Px {
 // main() for one output pixel                                                         taa.comp:708-960
 // WRITE_SCREEN = false: the screen result is left alone (fix-up of a fused frame, where the follow-on passes
 // already consumed the tuned kernel's on-chip result).
-template <bool WRITE_SCREEN>
-__device__ __forceinline__ void resolve_pixel_exact(const ResolveArgs& A, const int x, const int y) {
+// where the nine neighbourhood taps (and the current colour) come from: straight through the software sampler ...
+struct DirectTaps {
+	__device__ __forceinline__ f3 operator()(const Px& px, float2 off, int x, int y, float invw, float invh) const { return px.colour_tap(off, x, y, invw, invh); }
+};
+// ... or out of a shared-memory tile in which every texel's tap was evaluated once (SPEC = 1: the tap of texel (x, y) is a function of (x, y)
+// alone there — no unjitter offset, no upsampling —, so nine pixels share it; same function, same bits)
+struct TileTaps {
+	const float* tile;  // [3][TILE_H + 2][TILE_W + 2]
+	int x0, y0, w, h;   // texel of tile entry (1, 1); tile extent without the apron
+	__device__ __forceinline__ f3 operator()(const Px& px, float2 off, int x, int y, float invw, float invh) const {
+		// (x, y) is the pixel's own texel or a neighbour: uv_to_tc(tc_to_uv(x)) == x for every frame size below 2^22, so the tap is in the tile;
+		// the clamp only keeps an impossible index inside the array
+		const int i = min(max(x - x0 + 1, 0), w + 1), j = min(max(y - y0 + 1, 0), h + 1);
+		const int n = (w + 2) * (h + 2), k = j * (w + 2) + i;
+		return mk3(tile[k], tile[n + k], tile[2 * n + k]);
+	}
+};
+
+// SPEC = 1: the switch pattern of the reference's DEFAULT settings (taa.hpp:31-76: RGB, min / max box, clamp, bilinear history, velocity for
+// movers only and matrix reprojection for the rest, no rejection, no alpha modulation) folded at compile time. The code is this very function:
+// the folded switches only remove what those settings never execute.
+__device__ __forceinline__ void fold_reference_defaults(TaaParameters& P) {
+	P.mPassThrough = 0; P.mUseYCoCg = 0; P.mShrinkChromaAxis = 0; P.mVarianceClipping = 0; P.mShapedNeighbourhood = 0; P.mColorClampingOrClipping = 1;
+	P.mUnjitterNeighbourhood = 0; P.mUnjitterCurrentSample = 0; P.mToneMapLumaKaris = 0; P.mAddNoise = 0; P.mRayTraceAugment = 0;
+	P.mUseVelocityVectors = 1; P.mVelocitySampleMode = 0; P.mInterpolationMode = 0; P.mRejectOutside = 0; P.mDepthCulling = 0;
+	P.mDynamicAntiGhosting = 0; P.mVelBasedAlpha = 0; P.mLumaWeightingLottes = 0; P.mReduceBlendNearClamp = 0;
+}
+
+template <bool WRITE_SCREEN, int SPEC = 0, class TAPS = DirectTaps>
+__device__ __forceinline__ void resolve_pixel_exact(const ResolveArgs& A, const int x, const int y, const TAPS taps = TAPS()) {
 	unsigned int* st = A.status;
 
-	const TaaParameters& P = A.ubo.param[(A.ubo.splitScreen && x > A.ubo.splitX) ? 1 : 0];
+	TaaParameters Pl;
+	const TaaParameters* Pp = &A.ubo.param[(SPEC == 0 && A.ubo.splitScreen && x > A.ubo.splitX) ? 1 : 0];
+	if (SPEC == 1) { Pl = *Pp; fold_reference_defaults(Pl); Pp = &Pl; }
+	const TaaParameters& P = *Pp;
 	Px px(A, P);
 
 	const float u = ((float)x + 0.5f) / (float)A.out_w;  // tc_to_uv                       taa.comp:131
@@ -205,7 +237,7 @@ __device__ __forceinline__ void resolve_pixel_exact(const ResolveArgs& A, const 
 		st_r32ui(A.mask, x, y, 0u);
 		return;
 	}
-	if (A.ubo.mBypassHistoryUpdate) {  // taa.comp:732-737
+	if (SPEC == 0 && A.ubo.mBypassHistoryUpdate) {  // taa.comp:732-737
 		float4 h = fetch_rgba16f(A.history_in, A.out_w, A.out_h, x, y, st);
 		if (WRITE_SCREEN) st_rgba16f(A.result, x, y, make_float4(h.x, h.y, h.z, 1.f));
 		st_rgba16f(A.history_out, x, y, make_float4(h.x, h.y, h.z, 1.f));
@@ -219,15 +251,15 @@ __device__ __forceinline__ void resolve_pixel_exact(const ResolveArgs& A, const 
 	f3 colMin, colMax, clipTowards;
 	{
 		float2 off = P.mUnjitterNeighbourhood ? px.jitter_uv() : make_float2(0.f, 0.f);
-		f3 cC = px.colour_tap(off, lx, ly, invw, invh);
-		f3 c1 = px.colour_tap(off, lx - 1, ly - 1, invw, invh);
-		f3 c2 = px.colour_tap(off, lx, ly - 1, invw, invh);
-		f3 c3 = px.colour_tap(off, lx + 1, ly - 1, invw, invh);
-		f3 c4 = px.colour_tap(off, lx - 1, ly, invw, invh);
-		f3 c5 = px.colour_tap(off, lx + 1, ly, invw, invh);
-		f3 c6 = px.colour_tap(off, lx - 1, ly + 1, invw, invh);
-		f3 c7 = px.colour_tap(off, lx, ly + 1, invw, invh);
-		f3 c8 = px.colour_tap(off, lx + 1, ly + 1, invw, invh);
+		f3 cC = taps(px, off, lx, ly, invw, invh);
+		f3 c1 = taps(px, off, lx - 1, ly - 1, invw, invh);
+		f3 c2 = taps(px, off, lx, ly - 1, invw, invh);
+		f3 c3 = taps(px, off, lx + 1, ly - 1, invw, invh);
+		f3 c4 = taps(px, off, lx - 1, ly, invw, invh);
+		f3 c5 = taps(px, off, lx + 1, ly, invw, invh);
+		f3 c6 = taps(px, off, lx - 1, ly + 1, invw, invh);
+		f3 c7 = taps(px, off, lx, ly + 1, invw, invh);
+		f3 c8 = taps(px, off, lx + 1, ly + 1, invw, invh);
 		if (P.mVarianceClipping) {
 			const float N = 9.0f;
 			f3 m1 = cC + c1 + c2 + c3 + c4 + c5 + c6 + c7 + c8;
@@ -265,11 +297,11 @@ __device__ __forceinline__ void resolve_pixel_exact(const ResolveArgs& A, const 
 	// ---- current colour                                                              taa.comp:750-756
 	f3 cur;
 	float beta;
-	if (A.ubo.mUpsampling) {
+	if (SPEC == 0 && A.ubo.mUpsampling) {
 		cur = px.upsampled_colour(x, y, beta);
 	} else {
 		float2 off = P.mUnjitterCurrentSample ? px.jitter_uv() : make_float2(0.f, 0.f);
-		cur = px.colour_tap(off, lx, ly, invw, invh);
+		cur = taps(px, off, lx, ly, invw, invh);
 		beta = 1.0f;
 	}
 	const float depth = fetch_r32f(A.depth, A.in_w, A.in_h, lx, ly, st);
@@ -648,10 +680,52 @@ __global__ void __launch_bounds__(128) taa_resolve_fixup_kernel(const __grid_con
 	}
 }
 
-cudaError_t launch_resolve_generic(const ResolveArgs& args, cudaStream_t stream) {
+// The reference's default settings (BASELINE configs[0]) on the exact arithmetic: CTA = 32 x 8 pixels; the sampled colour of every texel of the
+// tile and its one-texel apron is evaluated once into shared memory (1.33 sampler evaluations per pixel instead of 10), then every pixel runs
+// resolve_pixel_exact with the default switches folded. Bit-identical to the general kernel by construction (tests/test_parity_gpu.py).
+constexpr int SPEC_W = 32, SPEC_H = 8, SPEC_N = (SPEC_W + 2) * (SPEC_H + 2);
+__global__ void __launch_bounds__(SPEC_W * SPEC_H) taa_resolve_defaults_kernel(const __grid_constant__ ResolveArgs A) {
+	__shared__ float tile[3 * SPEC_N];
+	const int x0 = blockIdx.x * SPEC_W, y0 = A.band_y0 + blockIdx.y * SPEC_H;
+	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+	{
+		TaaParameters Pl = A.ubo.param[0];
+		fold_reference_defaults(Pl);
+		Px px(A, Pl);
+		const float invw = 1.0f / (float)A.in_w, invh = 1.0f / (float)A.in_h;
+		const int yend = min(A.band_y0 + A.band_rows, A.out_h);  // rows below the band / image are nobody's neighbours but the last row's
+		for (int k = threadIdx.y * SPEC_W + threadIdx.x; k < SPEC_N; k += SPEC_W * SPEC_H) {
+			const int j = k / (SPEC_W + 2), i = k - j * (SPEC_W + 2);
+			const int tx = x0 - 1 + i, ty = y0 - 1 + j;
+			f3 c = mk3(0.f, 0.f, 0.f);
+			if (tx <= A.out_w && ty <= yend) c = px.colour_tap(make_float2(0.f, 0.f), tx, ty, invw, invh);
+			tile[k] = c.x; tile[SPEC_N + k] = c.y; tile[2 * SPEC_N + k] = c.z;
+		}
+	}
+	__syncthreads();
+	if (x >= A.out_w || y >= A.band_y0 + A.band_rows || y >= A.out_h) return;
+	TileTaps taps = {tile, x0, y0, SPEC_W, SPEC_H};
+	resolve_pixel_exact<true, 1, TileTaps>(A, x, y, taps);
+}
+
+// the call's settings are the reference's default switch pattern (fold_reference_defaults) and nothing else is asked for
+bool defaults_kernel_supports(const ResolveArgs& A) {
+	static const bool off = [] { const char* v = getenv("TAA_DEFAULTS_KERNEL"); return v && v[0] == '0'; }();  // A/B aid
+	const TaaUniforms& U = A.ubo;
+	const TaaParameters& P = U.param[0];
+	if (off || U.splitScreen || U.mUpsampling || U.mBypassHistoryUpdate) return false;
+	if (A.in_w != A.out_w || A.in_h != A.out_h || A.segmask.p) return false;
+	return !P.mPassThrough && !P.mUseYCoCg && !P.mVarianceClipping && !P.mShapedNeighbourhood && P.mColorClampingOrClipping == 1 && !P.mUnjitterNeighbourhood &&
+	       !P.mUnjitterCurrentSample && !P.mToneMapLumaKaris && !P.mAddNoise && !P.mRayTraceAugment && P.mUseVelocityVectors == 1 && P.mVelocitySampleMode == 0 &&
+	       P.mInterpolationMode == 0 && !P.mRejectOutside && !P.mDepthCulling && !P.mDynamicAntiGhosting && !P.mVelBasedAlpha && !P.mLumaWeightingLottes &&
+	       !P.mReduceBlendNearClamp;
+}
+
+cudaError_t launch_resolve_generic(const ResolveArgs& args, bool allow_specialised, cudaStream_t stream) {
 	dim3 block(32, 8);
 	dim3 grid((args.out_w + block.x - 1) / block.x, (args.band_rows + block.y - 1) / block.y);
-	taa_resolve_generic_kernel<<<grid, block, 0, stream>>>(args);
+	if (allow_specialised && defaults_kernel_supports(args)) taa_resolve_defaults_kernel<<<grid, block, 0, stream>>>(args);
+	else taa_resolve_generic_kernel<<<grid, block, 0, stream>>>(args);
 	return cudaGetLastError();
 }
 

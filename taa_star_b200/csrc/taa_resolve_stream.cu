@@ -1173,13 +1173,14 @@ int pick_rows(int nx, int band_rows, int resident, int rmax) {
 }
 
 // The unit geometry of a band of `band_rows` rows (see UnitGeo); halo_top / halo_bot > 0: the band has a neighbour on that side whose halo is that high
-UnitGeo unit_geometry(int nx, int band_rows, int resident, int rmax, bool hints_on, int halo_top, int halo_bot) {
+UnitGeo unit_geometry(int nx, int band_rows, int resident, int rmax, bool hints_on, int halo_top, int halo_bot, bool epilogue = false) {
 	const int R = pick_rows(nx, band_rows, resident, rmax);
 	// the last rows of the band in short units
 	// (measured on B200, 4K pan + one mover, R = 26: no hints, no tail 0.1033 ms; hints alone 0.1043; tail alone 0.1054; hints + 15 % tail in units of 14
 	// rows 0.0958; 25 %: 0.0960; 35 %: 0.0994; units of 8 rows: 0.0968 .. 0.1015)
 	static const int tail_env = [] { const char* v = getenv("TAA_STREAM_TAIL"); return v ? atoi(v) : -1; }();   // tuning aids
-	const int tail_pct = tail_env >= 0 ? tail_env : (hints_on ? 20 : 0);
+	// (a unit of the sharpening-epilogue variants resolves two extra rows: short units cost more there — measured 0.1733 ms at 10 %, 0.1742 at 20 %, 0.1809 at 0)
+	const int tail_pct = tail_env >= 0 ? tail_env : (hints_on ? (epilogue ? 10 : 20) : 0);
 	static const int rs_env = [] { const char* v = getenv("TAA_STREAM_RS"); return v ? atoi(v) : 0; }();
 	UnitGeo geo;
 	geo.nx = nx; geo.R = R;
@@ -1223,7 +1224,7 @@ cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const C
 	static const bool hints_off = [] { const char* v = getenv("TAA_STREAM_HINTS"); return v && v[0] == '0'; }();  // A/B aid
 	const bool hints_on = hints && !hints_off;
 	const bool up = PEER && peers->nb_hist[0], dn = PEER && peers->nb_hist[1];
-	const UnitGeo geo = unit_geometry(nx, A.band_rows, resident, rmax, hints_on, up ? peers->halo : 0, dn ? peers->halo : 0);
+	const UnitGeo geo = unit_geometry(nx, A.band_rows, resident, rmax, hints_on, up ? peers->halo : 0, dn ? peers->halo : 0, EPI != 0);
 	const int ny = geo.ny, R = geo.R;
 	PeerArgs pa = {};
 	if (PEER) {
@@ -1313,9 +1314,9 @@ cudaError_t launch_resolve_stream(const ResolveArgs& A, unsigned int* fix_list, 
 		static const int epi_minb = [] { const char* v = getenv("TAA_STREAM_EPI_MINB"); return v ? atoi(v) : 0; }();  // tuning aid
 		if (A.epilogue == 1) { if (alp) TAA_STREAM_EPI(true, 5, 1); TAA_STREAM_EPI(false, 5, 1); }
 		if (alp) TAA_STREAM_EPI(true, 5, 2);
-		if (epi_minb == 4) TAA_STREAM_EPI(false, 4, 2);
+		if (epi_minb == 6) TAA_STREAM_EPI(false, 6, 2);
 		if (epi_minb == 5) TAA_STREAM_EPI(false, 5, 2);
-		TAA_STREAM_EPI(false, 6, 2);  // (measured on B200, 4K: 0.162 ms at 6 CTAs / SM, 0.168 at 4, 0.180 at 5)
+		TAA_STREAM_EPI(false, 4, 2);  // (measured on B200, 4K: 0.168 ms at 4 pairs of warps per SM (203 registers), 0.173 at 6 (168 + spills), 0.187 at 5)
 #undef TAA_STREAM_EPI
 	}
 	if (rej) {

@@ -371,3 +371,48 @@ def test_band_halo_overflow_is_reported():
     ctx.resolve(u, color=sl(ins["color"]), depth=sl(ins["depth"]), velocity=sl(ins["velocity"]), history_in=sl(hist), history_out=(out, y0))
     assert ctx.poll_status() == abi.TAA_E_HALO_OVERFLOW
     assert ctx.poll_status() == abi.TAA_OK  # cleared by the read
+
+
+# ---- the reference's default settings (BASELINE configs[0]) on the specialised exact kernel -----------------------------------------------
+@pytest.mark.parametrize("size", [(256, 144), (1, 1), (33, 9), (31, 17), (97, 41), (640, 360)])
+def test_defaults_kernel_is_bit_identical(oracle, size):
+    """Default context flags + the reference's default switch pattern = taa_resolve_defaults_kernel (shared-memory colour taps, folded
+    switches). It is the general kernel's arithmetic: every output bit-identical to the oracle, masks and the debug image included; ragged
+    sizes, float parameters away from their defaults, history reset."""
+    w, h = size
+    sc = scene(w, h, pan_px=(2.75, -1.5))
+    f0, f1 = sc.frame(2), sc.frame(3)
+    for p, reset in ((configs.config1_defaults(), False), (with_params(configs.config1_defaults(), mAlpha=0.2, mDebugMode=2, mDebugScale=3.0), False),
+                     (configs.config1_defaults(), True)):
+        u = configs.uniforms_for(p, f1.jitter_ndc, reset_history=reset)
+        # matrices that move static pixels (the defaults reproject them with the matrices, taa.comp:426-430)
+        u.mHistoryViewProjMatrix[12] = 0.004
+        u.mHistoryViewProjMatrix[13] = -0.003
+        ctx = host.TaaContext((w, h))  # default flags: the specialised kernel is allowed
+        n0 = ctx.launch_count
+        check_exact(oracle, u, np_inputs(f1), random_history(h, w, 11), want=("history_out", "result", "mask", "debug"), ctx=ctx)
+        assert ctx.launch_count - n0 == 1
+        ctx.close()
+
+
+def test_defaults_kernel_equals_general_kernel_on_bands():
+    """Row bands of the specialised kernel (tile rows clipped at the band) against the general kernel on the whole frame, bit for bit."""
+    w, h = 320, 200
+    dev = torch.device("cuda")
+    sc = SyntheticScene(w, h, device=dev, with_aux=False)
+    f1 = sc.frame(5)
+    u = configs.uniforms_for(configs.config1_defaults(), f1.jitter_ndc)
+    hist = sc.frame(4).color.clone()
+    outs = {}
+    ctx = host.TaaContext((w, h), flags=abi.TAA_FLAG_EXACT)
+    outs["general"] = {k: torch.zeros(h, w, 4, dtype=torch.float16, device=dev) for k in ("history_out", "result")}
+    ctx.resolve(u, color=f1.color, depth=f1.depth, velocity=f1.velocity, history_in=hist, **outs["general"])
+    ctx.close()
+    outs["bands"] = {k: torch.zeros(h, w, 4, dtype=torch.float16, device=dev) for k in ("history_out", "result")}
+    for a, b in ((0, 67), (67, 70), (70, 200)):
+        c = host.TaaContext((w, h), band=(a, b - a))
+        c.resolve(u, color=f1.color, depth=f1.depth, velocity=f1.velocity, history_in=hist, **outs["bands"])
+        c.close()
+    torch.cuda.synchronize()
+    for k in ("history_out", "result"):
+        assert torch.equal(outs["general"][k].view(torch.int16), outs["bands"][k].view(torch.int16)), k
