@@ -12,5 +12,5 @@ echo "== 8K nccl N=$N"; TAA_SHARDED_EXCHANGE=nccl timeout 600 $TR --master-port 
 echo "== 8K replicate N=$N"; timeout 600 $TR --master-port 29514 bench.py --gpus $N --steps 48 --warmup 5 --replicate --no-verify 2>&1 | f
 echo "== 16K peer N=$N"; timeout 600 $TR --master-port 29515 bench.py --gpus $N --steps 48 --warmup 5 --width 15360 --height 8640 --no-verify 2>&1 | f
 echo "== config 5 N=$N"; timeout 600 $TR --master-port 29516 bench.py --gpus $N --config 5 --steps 48 --warmup 5 2>&1 | f
-} > gpurun_out/r2u_n$N.log 2>&1
-cat gpurun_out/r2u_n$N.log
+} > gpurun_out/suite_n$N.log 2>&1
+cat gpurun_out/suite_n$N.log

@@ -5,6 +5,26 @@
 
 namespace taa {
 
+// The settings family of the tuned kernels (BASELINE configs 2-5): YCoCg, variance box, clipAabb, Catmull-Rom history, velocity for everything;
+// whole-frame or band, equal input and output size, buffers below 4 GB (the kernels address with 32-bit offsets).
+bool tuned_supports(const ResolveArgs& A) {
+	const TaaUniforms& U = A.ubo;
+	const TaaParameters& P = U.param[0];
+	if (U.splitScreen || U.mUpsampling || U.mBypassHistoryUpdate) return false;
+	if (A.in_w != A.out_w || A.in_h != A.out_h) return false;
+	if ((long long)A.out_w * A.out_h >= (1ll << 32)) return false;
+	const Img* ins[] = {&A.color, &A.depth, &A.velocity, &A.history_in};
+	const ImgW* outs[] = {&A.history_out, &A.result, &A.mask};
+	for (const Img* i : ins) if (i->p && (long long)i->rows * i->pitch >= (1ll << 32)) return false;  // 32-bit offsets in the kernel
+	for (const ImgW* o : outs) if (o->p && ((long long)o->rows * o->pitch >= (1ll << 32) || o->y0 > A.band_y0)) return false;
+	if (A.debug.p || A.segmask.p) return false;
+	if (P.mPassThrough || !P.mUseYCoCg || P.mShrinkChromaAxis || !P.mVarianceClipping || P.mColorClampingOrClipping != 2) return false;
+	if (P.mUnjitterNeighbourhood || P.mUnjitterCurrentSample || P.mToneMapLumaKaris || P.mAddNoise || P.mRayTraceAugment) return false;
+	if (P.mUseVelocityVectors != 2 || P.mVelocitySampleMode != 0 || P.mInterpolationMode != 2) return false;
+	if (P.mDepthCulling && !A.history_depth.p) return false;
+	return true;
+}
+
 static cudaError_t ensure_fix_buffers(taa_ctx* c) {
 	if (c->fix_list) return cudaSuccess;
 	cudaError_t e = cudaMalloc(&c->fix_list, (size_t)c->desc.out_width * c->desc.band_rows * sizeof(unsigned int));
@@ -25,7 +45,6 @@ cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, i
 		const TaaParameters& P = A.ubo.param[0];
 		const bool fixup_all = (c->desc.flags & TAA_FLAG_FIXUP_ALL) != 0;
 		const bool need_fixup = fixup_all || A.mask.p != nullptr || P.mDynamicAntiGhosting;
-		static const bool tile = [] { const char* v = getenv("TAA_TUNED_VARIANT"); return v && v[0] == 't'; }();  // A/B aid: the 32x32-tile kernel
 		unsigned int *list = nullptr, *cnt = nullptr, *cnt_next = nullptr;
 		if (need_fixup) {
 			cudaError_t e = ensure_fix_buffers(c);
@@ -35,7 +54,7 @@ cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, i
 			cnt_next = c->fix_count + (c->fix_parity ^ 1);
 			c->fix_parity ^= 1;
 		}
-		const bool streaming = !tile && stream_supports(A);
+		const bool streaming = stream_supports(A);
 		if (streaming && !c->hints) {  // (a failed allocation only costs the ordering hint)
 			if (cudaMalloc(&c->hints, stream_hint_bytes()) == cudaSuccess) cudaMemsetAsync(c->hints, 0, stream_hint_bytes(), s);
 			else { c->hints = nullptr; cudaGetLastError(); }
@@ -58,9 +77,8 @@ cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, i
 			c->peers.first = false;
 			peers = &sp;
 		}
-		cudaError_t e = tile ? launch_resolve_tuned(A, list, cnt, cnt_next, fixup_all, s)
-		                     : streaming ? launch_resolve_stream(A, list, cnt, cnt_next, fixup_all, c->num_sms, c->hints, c->hint_phase++, peers, s)
-		                                 : launch_resolve_strip(A, list, cnt, cnt_next, fixup_all, s);
+		cudaError_t e = streaming ? launch_resolve_stream(A, list, cnt, cnt_next, fixup_all, c->num_sms, c->hints, c->hint_phase++, peers, s)
+		                          : launch_resolve_strip(A, list, cnt, cnt_next, fixup_all, s);
 		if (c->hint_phase >= 3 * 1024) c->hint_phase -= 3 * 1024;
 		if (e != cudaSuccess) return e;
 		*launched = 1;

@@ -14,12 +14,10 @@ bool defaults_kernel_supports(const ResolveArgs& args);
 cudaError_t launch_resolve_fixup(const ResolveArgs& args, const unsigned int* list, const unsigned int* count, bool write_screen, int num_sms,
                                  cudaStream_t stream);
 
-// taa.comp for the BASELINE configs 2-5 family of settings, tiled through shared memory (taa_resolve_tuned.cu).
-// Appends the pixels whose `rectified` bit needs the exact arithmetic to fix_list / *fix_count and zeroes *fix_count_next.
+// The BASELINE configs 2-5 family of settings (taa_dispatch.cu). The tuned kernels append the pixels whose `rectified` bit (or anti-ghosting
+// predicate) needs the exact arithmetic to fix_list / *fix_count and zero *fix_count_next.
 bool tuned_supports(const ResolveArgs& args);
-cudaError_t launch_resolve_tuned(const ResolveArgs& args, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next,
-                                 bool fixup_all, cudaStream_t stream);
-// the same contract with long column strips and a history window that runs one row ahead (taa_resolve_strip.cu): the default
+// 64-wide shared-memory tiles, long column strips and a history window that runs one row ahead (taa_resolve_strip.cu): the rejection variants
 cudaError_t launch_resolve_strip(const ResolveArgs& args, unsigned int* fix_list, unsigned int* fix_count, unsigned int* fix_count_next,
                                  bool fixup_all, cudaStream_t stream);
 

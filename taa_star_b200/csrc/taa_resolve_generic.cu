@@ -1,7 +1,7 @@
 // taa_resolve_generic.cu — the EXACT, fully general resolve kernel: every switch of `Parameters`
 // (shaders/taa.comp:50-95) is a warp-uniform runtime branch. One thread per output pixel.
 // It exists so that ANY settings block the reference accepts runs on the GPU; the tuned kernels in
-// taa_resolve_tuned.cu cover the BASELINE configs. Compiled with --fmad=false (see taa_device.cuh).
+// taa_resolve_stream.cu / taa_resolve_strip.cu cover the BASELINE configs. Compiled with --fmad=false (see taa_device.cuh).
 #include "taa_device.cuh"
 #include "taa_kernels.h"
 #include <cstdlib>
@@ -663,7 +663,7 @@ __device__ __forceinline__ void resolve_pixel_exact_family(const ResolveArgs& A,
 	st_r32ui(A.mask, x, y, (rejected ? 1u : 0u) | (rectified ? 2u : 0u) | (2u << 2));
 }
 
-// Fix-up pass of the tuned kernels (taa_resolve_tuned.cu): the pixels whose `rectified` predicate
+// Fix-up pass of the tuned kernels (taa_resolve_stream.cu, taa_resolve_strip.cu): the pixels whose `rectified` predicate
 // (taa.comp:845) the re-associated arithmetic could not decide safely are recomputed here with the
 // exact arithmetic, from the inputs alone. `list` holds pixels packed as y * out_w + x.
 template <bool WRITE_SCREEN>

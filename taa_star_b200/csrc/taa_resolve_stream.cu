@@ -1265,7 +1265,7 @@ extern "C" __attribute__((visibility("default"))) int taa_debug_stream_trace(voi
 #endif
 
 bool stream_supports(const ResolveArgs& A) {
-	static const bool off = [] { const char* v = getenv("TAA_TUNED_VARIANT"); return v && (v[0] == 's' || v[0] == 't'); }();  // "strip" / "tile": A/B partners
+	static const bool off = [] { const char* v = getenv("TAA_TUNED_VARIANT"); return v && v[0] == 's'; }();  // "strip": the A/B partner
 	if (off || !encode_fn()) return false;
 	const TaaParameters& P = A.ubo.param[0];
 	// The rejection variants (config 3) still run faster on the strip kernel (0.216 against 0.369 ms per 4K frame on B200): their uniform-motion

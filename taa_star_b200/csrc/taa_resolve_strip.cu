@@ -1,6 +1,7 @@
-// taa_resolve_strip.cu — the staged, long-strip variant of the tuned resolve kernel (same settings family and the same
-// arithmetic contract as taa_resolve_tuned.cu: exact coordinates and predicates, re-associated colour filtering, exact
-// fix-up list). It is the default; taa_resolve_tuned.cu stays as the A/B partner (TAA_TUNED_VARIANT=tile).
+// taa_resolve_strip.cu — the staged, long-strip tuned resolve kernel (settings family: tuned_supports() in taa_dispatch.cu; arithmetic contract:
+// exact coordinates and predicates, re-associated colour filtering, undecidable pixels handed to the exact fix-up list).
+// Since round 2 it serves the REJECTION variants of the family (config 3) and images that tensor maps cannot describe; everything else runs on
+// the streaming kernel (taa_resolve_stream.cu). The 32x32-tile kernel it replaced in round 1 is gone (its numbers: profiles/r01_b_*, r01_c_*).
 //
 // What is different is the shape of the work, chosen against what ncu shows for the tile kernel (issue-bound at ~470 warp
 // instructions per pixel, and behind that stalled on the latency of first-touch loads):

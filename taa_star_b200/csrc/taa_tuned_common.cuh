@@ -1,5 +1,6 @@
-// taa_tuned_common.cuh — building blocks shared by the tuned resolve kernels (taa_resolve_tuned.cu: 32x32 tiles, 4-pixel strips;
-// taa_resolve_strip.cu: 64-wide tiles, long strips). See taa_resolve_tuned.cu for the arithmetic contract.
+// taa_tuned_common.cuh — building blocks shared by the tuned resolve kernels (taa_resolve_stream.cu: one warp per 62-column strip, rows
+// streamed through TMA; taa_resolve_strip.cu: 64-wide shared-memory tiles, long strips). Arithmetic contract: DESIGN.md "Why the tuned kernels
+// are exact where it matters".
 #pragma once
 #include "taa_device.cuh"
 #include <cmath>

@@ -511,6 +511,9 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
     if clocks:
         clocks.region(False)
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    per_rank = [torch.zeros_like(ms) for _ in range(world)]
+    dist.all_gather(per_rank, ms)
+    per_rank_ms = [round(float(t.item()) / args.steps, 5) for t in per_rank]  # each rank's own device time per step (content differs per band)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = torch.tensor([sh.launch_count - launches0 if graphs is None else launches_per_cycle * args.steps // (2 * NSETS)], device=dev)
@@ -580,6 +583,7 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
                        "launch": graph_note,
                        "l2": f"inputs larger than L2: {NSETS} frame sets rotated, history ping-pong"},
             "gpu_launches": int(launches.item()), "gpu_launches_per_step_and_rank": round(lps, 2),
+            "per_rank_ms_per_step": per_rank_ms,
             "single_gpu_same_frame_ms": round(single_ms, 5) if single_ms is not None else None,
             "strong_scaling_efficiency_vs_same_frame": round(single_ms / ms_per_step / world, 4) if single_ms is not None else None,
             "sharded_vs_whole_frame": None if same is None else {"within_parity_bar": same, "differing_texels": ndiff, "max_abs_diff": maxd,

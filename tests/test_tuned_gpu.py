@@ -343,19 +343,6 @@ def test_uniform_tiles_next_to_a_mover_and_history_alpha(oracle):
     check_tuned(oracle, u, ins, hist, hist_depth=f0.depth.numpy())
 
 
-def test_tile_kernel_variant_in_a_subprocess():
-    """The 32x32-tile kernel (TAA_TUNED_VARIANT=tile, the A/B partner of the strip kernel) honours the same contract."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, TAA_TUNED_VARIANT="tile")
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_tuned_gpu.py"), "-q", "-x", "-m", "gpu", "-k",
-                        "test_single_frame or test_tiny_and_ragged_sizes or test_extreme_and_non_finite_motion or test_fixup_pass_is_bit_exact"],
-                       env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-
-
 @pytest.mark.parametrize("env", [dict(TAA_TUNED_VARIANT="strip"), dict(TAA_STREAM_REJ="1")], ids=["strip", "stream-rej"])
 def test_other_kernels_of_the_family_in_a_subprocess(env):
     """The default dispatch sends the plain variants to the streaming kernel and the rejection variants to the strip kernel. The other
