@@ -341,6 +341,7 @@ def run_single(args):
     torch.cuda.synchronize()
     clocks.region(True)
     e2e_launch0 = t.launch_count
+    e2e_h2d0 = t.h2d_bytes
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         n = 6 + k
@@ -353,7 +354,7 @@ def run_single(args):
     e2e_dt = time.perf_counter() - t0
     clocks.region(False)
     e2e_mpx = e2e_steps * px / e2e_dt / 1e6
-    h2d = px * (8 + 4 + 8)
+    h2d = (t.h2d_bytes - e2e_h2d0) // e2e_steps  # counted by the library from the copies it issued (colour + velocity; + depth when a kernel reads it)
     d2h = px * 8
     checksum = float(houts[(6 + e2e_steps - 1) % 3][::97, ::89, :3].float().mean())
     assert 0.05 < checksum < 0.95, f"implausible result mean {checksum}"
@@ -381,7 +382,8 @@ def run_single(args):
         "e2e": {"value": round(e2e_mpx, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "fps": round(e2e_steps / e2e_dt, 1), "path": "taa_invokee_frame_host: pinned host G-buffer -> H2D -> render() -> D2H of the final image, 3 frames in flight",
                 "gpu_launches": int(t.launch_count - e2e_launch0),
-                "bound": "PCIe: 166 MB up + 66 MB down per 4K frame at ~55-60 GB/s each way; the kernel is ~4 % of the frame time"},
+                "bound": f"PCIe: {h2d / 1e6:.0f} MB up + {d2h / 1e6:.0f} MB down per frame at ~55-60 GB/s each way; the kernel is ~4 % of the frame time",
+                "inputs_uploaded": "colour + velocity" + (" + depth" if h2d >= px * 20 else " (depth stays on the host: no kernel of this configuration reads it)")},
         "clocks": clocks.result(),
     }
     line.update(extra)

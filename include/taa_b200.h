@@ -427,6 +427,9 @@ enum { TAA_IMG_RESULT = 0, TAA_IMG_HISTORY = 1, TAA_IMG_DEBUG = 2, TAA_IMG_POSTP
 TAA_API void* taa_invokee_image(taa_invokee* t, int32_t which, int32_t slot);
 /* kernels launched by this invokee so far */
 TAA_API long long taa_invokee_launch_count(const taa_invokee* t);
+/* bytes taa_invokee_frame_host has copied host -> device so far. Depth (4 of the 20 bytes per pixel) is uploaded only when a dispatch of the
+ * frame can read it (depth culling, matrix reprojection, closest-depth velocity, segmentation mask); bench.py reports the per-frame delta. */
+TAA_API long long taa_invokee_h2d_bytes(const taa_invokee* t);
 /* the uniforms the last update()/render() produced (for parity tests against the oracle) */
 TAA_API const TaaUniforms* taa_invokee_uniforms(const taa_invokee* t);
 

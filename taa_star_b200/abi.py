@@ -161,6 +161,7 @@ SIGNATURES = {
     "taa_invokee_frame_host": (C.c_int, [_vp, C.c_int64, _P(taa_source_views), _P(_f32), _P(_f32), _f32, _f32, _f32, _vp]),
     "taa_invokee_wait": (C.c_int, [_vp, C.c_int64]),
     "taa_invokee_launch_count": (_ll, [_vp]),
+    "taa_invokee_h2d_bytes": (_ll, [_vp]),
     "taa_settings_write_ini": (C.c_int32, [_P(TaaParameters), _P(taa_invokee_settings), _P(TaaPostProcessPush), C.c_char_p, C.c_int32]),
     "taa_settings_read_ini": (C.c_int, [C.c_char_p, _P(TaaParameters), _P(taa_invokee_settings), _P(TaaPostProcessPush), _P(_f32), C.c_int32]),
     "taa_settings_ini_last_error": (C.c_char_p, []),

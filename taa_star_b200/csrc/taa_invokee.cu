@@ -53,6 +53,7 @@ struct taa_invokee {
 	cudaStream_t sUp = nullptr, sCompute = nullptr, sDown = nullptr;
 	std::vector<cudaEvent_t> evUploaded, evComputed, evDone;
 	std::vector<char> slotBusy;
+	long long h2dBytes = 0;             // bytes taa_invokee_frame_host has uploaded so far (depth only when a kernel of the frame reads it)
 	std::vector<taa_source_views> dsrc;  // device copies of host G-buffers
 	bool owns_dsrc = false;
 };
@@ -207,6 +208,7 @@ taa_invokee_settings* taa_invokee_settings_ptr(taa_invokee* t) { return t ? &t->
 TaaPostProcessPush* taa_invokee_postprocess(taa_invokee* t) { return t ? &t->mPostProcessPushConstants : nullptr; }
 const TaaUniforms* taa_invokee_uniforms(const taa_invokee* t) { return t ? &t->mTaaUniforms : nullptr; }
 long long taa_invokee_launch_count(const taa_invokee* t) { return (t && t->ctx) ? taa_launch_count(t->ctx) : 0; }
+long long taa_invokee_h2d_bytes(const taa_invokee* t) { return t ? t->h2dBytes : 0; }
 
 // writeSettingsToIni / readSettingsFromIni (taa.hpp:1198-1339) on the invokee's own members; taa_ini.cu holds the format
 int32_t taa_invokee_write_settings_ini(taa_invokee* t, char* out, int32_t cap) {
@@ -461,7 +463,18 @@ int taa_invokee_frame_host(taa_invokee* t, int64_t frame, const taa_source_views
 	const size_t px = (size_t)t->in_w * t->in_h;
 	const taa_source_views& d = t->dsrc[i];
 	if ((e = cudaMemcpyAsync((void*)d.color, hv->color, px * 8, cudaMemcpyHostToDevice, t->sUp)) != cudaSuccess) return inv_cuda(t, e, "H2D colour");
-	if ((e = cudaMemcpyAsync((void*)d.depth, hv->depth, px * 4, cudaMemcpyHostToDevice, t->sUp)) != cudaSuccess) return inv_cuda(t, e, "H2D depth");
+	// Depth is uploaded when a dispatch of this frame can read it: taa.comp touches uCurrentDepth for the matrix reprojection of pixels
+	// without a usable velocity (taa.comp:421-430), the closest-depth velocity mode (:399-404), depth culling (:815-823, also as the NEXT
+	// frame's history depth) and the segmentation mask (:640). With velocity for everything and none of those (BASELINE config 2) no kernel reads
+	// it, and 4 of the 20 bytes per pixel stay off the PCIe link. After a settings change that starts to need depth the first frame
+	// sees the last uploaded depth as its history depth — the reference resets the history on such a change (mResetHistoryOnChange).
+	bool need_depth = false;
+	for (int k = 0; k < (t->S.mSplitScreen ? 2 : 1); ++k) {
+		const TaaParameters& P = t->mParameters[k];
+		need_depth = need_depth || P.mDepthCulling || P.mUseVelocityVectors != 2 || P.mVelocitySampleMode == 2 || P.mRayTraceAugment;
+	}
+	t->h2dBytes += (long long)px * (8 + 8 + (need_depth ? 4 : 0)) + ((d.uvnrm && hv->uvnrm) ? (long long)px * 16 : 0) + ((d.matid && hv->matid) ? (long long)px * 4 : 0);
+	if (need_depth && (e = cudaMemcpyAsync((void*)d.depth, hv->depth, px * 4, cudaMemcpyHostToDevice, t->sUp)) != cudaSuccess) return inv_cuda(t, e, "H2D depth");
 	if ((e = cudaMemcpyAsync((void*)d.velocity, hv->velocity, px * 8, cudaMemcpyHostToDevice, t->sUp)) != cudaSuccess) return inv_cuda(t, e, "H2D velocity");
 	if (d.uvnrm && hv->uvnrm && (e = cudaMemcpyAsync((void*)d.uvnrm, hv->uvnrm, px * 16, cudaMemcpyHostToDevice, t->sUp)) != cudaSuccess) return inv_cuda(t, e, "H2D uvnrm");
 	if (d.matid && hv->matid && (e = cudaMemcpyAsync((void*)d.matid, hv->matid, px * 4, cudaMemcpyHostToDevice, t->sUp)) != cudaSuccess) return inv_cuda(t, e, "H2D matid");

@@ -345,6 +345,11 @@ class Taa:
         return int(self._lib.taa_invokee_launch_count(self._h))
 
     # ---- host-buffer frames ----
+    @property
+    def h2d_bytes(self) -> int:
+        """Bytes frame_host has uploaded so far (depth travels only when a kernel of the frame reads it)."""
+        return int(self._lib.taa_invokee_h2d_bytes(self._h))
+
     def frame_host(self, frame_id: int, color: torch.Tensor, depth: torch.Tensor, velocity: torch.Tensor, view, proj, out_final: torch.Tensor,
                    time_s: float = 0.0, cam_near: float = 0.1, cam_far: float = 100.0, uvnrm=None, matid=None):
         v = taa_source_views(color.data_ptr(), depth.data_ptr(), uvnrm.data_ptr() if uvnrm is not None else None, velocity.data_ptr(),
