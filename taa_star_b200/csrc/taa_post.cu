@@ -210,15 +210,28 @@ cudaError_t launch_blit_nearest(const PostImg& io, int src_w, int src_h, cudaStr
 	blit_nearest_kernel<<<grid2d(io.w, io.h, b), b, 0, stream>>>(io, src_w, src_h);
 	return cudaGetLastError();
 }
+// images whose rows can be moved 16 bytes (two texels) at a time take the streaming pass (same values, alpha = 1 like sharpen_at / cas_at)
+static bool rows_kernel_ok(const PostImg& io) {
+	return (io.w & 1) == 0 && (((unsigned long long)io.src.p | (unsigned long long)io.src.pitch | (unsigned long long)io.dst.p | (unsigned long long)io.dst.pitch) & 15ull) == 0ull;
+}
+constexpr int ROWS_RUN = 32;  // rows per warp of the streaming pass: two halo rows per 32
 cudaError_t launch_sharpen(const PostImg& io, float factor, cudaStream_t stream) {
+	if (rows_kernel_ok(io)) {
+		sharpen_rows_kernel<1><<<dim3((io.w + 255) / 256, (io.h + ROWS_RUN - 1) / ROWS_RUN), 128, 0, stream>>>(io, factor, ROWS_RUN);
+		return cudaGetLastError();
+	}
 	dim3 b(32, 8);
 	sharpen_kernel<<<grid2d(io.w, io.h, b), b, 0, stream>>>(io, factor);
 	return cudaGetLastError();
 }
 cudaError_t launch_cas(const PostImg& io, const TaaCasPush& pc, cudaStream_t stream) {
-	dim3 b(32, 8);
 	float peak;
 	memcpy(&peak, &pc.const1[0], 4);
+	if (rows_kernel_ok(io)) {
+		sharpen_rows_kernel<2><<<dim3((io.w + 255) / 256, (io.h + ROWS_RUN - 1) / ROWS_RUN), 128, 0, stream>>>(io, peak, ROWS_RUN);
+		return cudaGetLastError();
+	}
+	dim3 b(32, 8);
 	cas_kernel<<<grid2d(io.w, io.h, b), b, 0, stream>>>(io, peak);
 	return cudaGetLastError();
 }
@@ -230,9 +243,8 @@ cudaError_t launch_post_process(const PostImg& io, const TaaPostProcessPush& pc,
 cudaError_t launch_sharpen_post(const PostImg& io, int sharpener, float sharpeningFactor, const TaaCasPush& cas, const TaaPostProcessPush& pc, cudaStream_t stream) {
 	// post_process.comp only copies (no zoom, no splitter, no debug view) and the rows can be moved 16 bytes at a time: the streaming pass
 	const bool identity = !pc.zoom && pc.splitX < 0 && !pc.debugL_show;
-	const bool aligned = (io.w & 1) == 0 && (((unsigned long long)io.src.p | (unsigned long long)io.src.pitch | (unsigned long long)io.dst.p | (unsigned long long)io.dst.pitch) & 15ull) == 0ull;
-	if (identity && aligned && (sharpener == 1 || sharpener == 2)) {
-		const int run = 32;  // rows per warp: two halo rows per 32
+	if (identity && rows_kernel_ok(io) && (sharpener == 1 || sharpener == 2)) {
+		const int run = ROWS_RUN;
 		const dim3 grid((io.w + 255) / 256, (io.h + run - 1) / run);
 		if (sharpener == 1) sharpen_rows_kernel<1><<<grid, 128, 0, stream>>>(io, sharpeningFactor, run);
 		else {

@@ -109,8 +109,20 @@ class ShardedTaa:
         rows = (height if replicate else L.hy1 - L.hy0)
         self.hist_y0 = 0 if replicate else L.hy0
         if self.peer:
-            self._peer_setup(rows, flags)
-            return
+            # every rank must end up in the same mode: if any rank cannot map its neighbours (no peer access between the GPUs, IPC refused),
+            # all of them fall back to the NCCL exchange
+            ok, why = 1, ""
+            try:
+                self._peer_setup(rows, flags)
+            except Exception as e:  # noqa: BLE001
+                ok, why = 0, f"{type(e).__name__}: {e}"
+            flag = torch.tensor([ok], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 1:
+                self.peer_reset()
+                return
+            self.peer = False
+            self.peer_fallback_reason = why or "another rank could not map its neighbours"
         self.hist = [torch.zeros(rows, width, 4, dtype=torch.float16, device=self.device) for _ in range(2)]
         self.result = torch.zeros(L.rows, width, 4, dtype=torch.float16, device=self.device)
         self.band_tmp = torch.zeros(L.rows, width, 4, dtype=torch.float16, device=self.device) if replicate else None
@@ -149,16 +161,16 @@ class ShardedTaa:
         lib = abi.load_library()
         self._lib = lib
         hbytes = rows * W * 8
+        handle = (C.c_ubyte * abi.TAA_IPC_HANDLE_BYTES)()
         self._arena = lib.taa_device_alloc(2 * hbytes + 4 * abi.TAA_BAND_FLAG_WORDS)
-        assert self._arena, "taa_device_alloc failed"
+        local_ok = bool(self._arena) and lib.taa_ipc_export(self._arena, handle) == abi.TAA_OK
+        mine = dict(ok=local_ok, handle=bytes(handle), hbytes=hbytes, hy0=L.hy0, band_rows=L.rows)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)  # (the only collective in here: every rank reaches it, whatever failed locally)
+        if not all(e["ok"] for e in everyone):
+            raise RuntimeError("a rank could not allocate or export its band buffers")
         self.hist = [host.tensor_from_ptr(self._arena + k * hbytes, (rows, W, 4), torch.float16) for k in range(2)]
         self._flags_ptr = self._arena + 2 * hbytes
-        handle = (C.c_ubyte * abi.TAA_IPC_HANDLE_BYTES)()
-        st = lib.taa_ipc_export(self._arena, handle)
-        assert st == abi.TAA_OK, "taa_ipc_export failed"
-        mine = dict(handle=bytes(handle), hbytes=hbytes, hy0=L.hy0, band_rows=L.rows)
-        everyone = [None] * self.world
-        dist.all_gather_object(everyone, mine, group=self.group)
         self._mapped = []
         peers = [None, None]
         for sd, nb in enumerate((self.rank - 1, self.rank + 1)):
@@ -185,7 +197,6 @@ class ShardedTaa:
         self.parity = 0
         self._pending = []
         self._capturing = self._ev_comm_captured = self._comm_in_capture = False
-        self.peer_reset()
 
     def peer_reset(self):
         """(Re)starts a frame sequence: flag blocks zeroed, the next step waits for nobody. Collective (a barrier on each side)."""
@@ -580,6 +591,7 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
                                     "peer stores: the resolve kernel writes its first / last halo rows into the neighbours' halos over NVLink and signals a flag; "
                                     "the neighbours' boundary units of the next frame wait on it (taa_band_peers) - one launch per band and frame, no collective" if sh.peer else
                                     "NCCL send/recv of 2 x halo rows of history per neighbour per frame, overlapped with the interior resolve"),
+                       "peer_fallback": getattr(sh, "peer_fallback_reason", None),
                        "launch": graph_note,
                        "l2": f"inputs larger than L2: {NSETS} frame sets rotated, history ping-pong"},
             "gpu_launches": int(launches.item()), "gpu_launches_per_step_and_rank": round(lps, 2),
