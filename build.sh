@@ -10,14 +10,16 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 FLAGS="-O3 -std=c++17 -lineinfo --fmad=false -Xcompiler -fPIC,-fvisibility=hidden -ccbin /usr/bin/g++ ${EXTRA_NVCC_FLAGS:-}"
 mkdir -p build
 objs=()
+pids=()
 for f in $SRC/*.cu; do
   o=build/$(basename "${f%.cu}").o
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find $SRC include -newer "$o" \( -name '*.h' -o -name '*.cuh' \) -print -quit)" ]; then
     echo "nvcc $f"
     $NVCC $ARCH $FLAGS -c "$f" -o "$o" &
+    pids+=($!)
   fi
   objs+=("$o")
 done
-wait
+for p in "${pids[@]:-}"; do [ -z "$p" ] || wait "$p" || { echo "build.sh: a compilation failed" >&2; exit 1; }; done
 $NVCC $ARCH -shared -o $OUT "${objs[@]}" -Xcompiler -fPIC -ccbin /usr/bin/g++
 echo "built $OUT"

@@ -4,7 +4,7 @@ import numpy as np, torch
 sys.path.insert(0, os.getcwd())
 from taa_star_b200 import abi, configs, host
 from taa_star_b200.synth import SyntheticScene
-W, H = 3840, 2160
+W, H = int(os.environ.get("W", 3840)), int(os.environ.get("H", 2160))
 dev = torch.device("cuda:0")
 mover = os.environ.get("MOVER", "1") == "1"
 sc = SyntheticScene(W, H, device=dev, with_aux=False)

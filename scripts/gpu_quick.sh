@@ -1,12 +1,20 @@
 #!/bin/bash
-# quick GPU session: all parity tests, the bench line, a few A/B lines given as "ENV=.. ENV=.. -- bench args" in $AB (one per line)
+# quick GPU session: parity tests of the default path, kernel-only A/B lines
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+b() { timeout 300 python bench.py --kernel-only --steps 100 --warmup 6 "$@" 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['frac'], d['motion'])"; }
 {
-echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q --timeout=900 --tb=short 2>&1 | grep -E "^(FAILED|ERROR|E  )|passed|failed" | cut -c1-260 | head -30
-echo "== bench"; timeout 900 python bench.py --steps 100 --warmup 5 2>/dev/null | tail -1 > gpurun_out/quick_bench_line.json; python -c "
-import json; d=json.load(open('gpurun_out/quick_bench_line.json')); print({k:d[k] for k in ('ms_per_step','value','e2e','gpu_launches')}); print({k:(d[k]['ms_per_step'],d[k]['frac']) for k in ('varying_motion','config1_defaults','config3_full_chain','config3_resolve_only','fused_resolve_cas')})"
-for mb in 4 5 6; do echo "== cfg3 stream-rej minb $mb"; TAA_STREAM_REJ=1 TAA_STREAM_MINB=$mb timeout 300 python bench.py --kernel-only --config 3 --steps 100 --warmup 5 2>&1 | tail -1 | cut -c1-200; done
-echo "== cfg3 strip"; timeout 300 python bench.py --kernel-only --config 3 --steps 100 --warmup 5 2>&1 | tail -1 | cut -c1-200
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+echo "== pytest tuned+chain+streams"; timeout 1500 python -m pytest tests/test_tuned_gpu.py tests/test_chain_gpu.py tests/test_streams.py -m gpu -q --timeout=900 --tb=short 2>&1 | grep -E "^(FAILED|ERROR|E  )|passed|failed" | cut -c1-260 | head -30
+echo "-- pan persist"; b
+echo "-- pan persist off"; TAA_STREAM_PERSIST=0 b
+echo "-- varying persist"; b --motion varying
+echo "-- varying persist off"; TAA_STREAM_PERSIST=0 b --motion varying
+echo "-- pan persist tail 0"; TAA_STREAM_TAIL=0 b
+echo "-- pan persist tail 0 R 20"; TAA_STREAM_TAIL=0 TAA_STREAM_R=20 b
+echo "-- pan persist tail 0 R 16"; TAA_STREAM_TAIL=0 TAA_STREAM_R=16 b
+echo "-- pan persist R 20"; TAA_STREAM_R=20 b
+echo "== fused"; timeout 300 python scripts/debug/fused_time.py 2>&1 | tail -1
+echo "== fused persist off"; TAA_STREAM_PERSIST=0 timeout 300 python scripts/debug/fused_time.py 2>&1 | tail -1
 } > gpurun_out/quick.log 2>&1
 cat gpurun_out/quick.log
