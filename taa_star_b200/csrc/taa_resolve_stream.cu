@@ -1326,6 +1326,7 @@ cudaError_t launch_resolve_stream(const ResolveArgs& A, unsigned int* fix_list, 
 	}
 	if (diag) { if (alp) TAA_STREAM_GO(false, true, true, 0, 6); TAA_STREAM_GO(false, false, true, 0, 6); }
 	if (alp) TAA_STREAM_GO(false, true, false, 0, 6);
+	if (minb_env == 7) TAA_STREAM_GO(false, false, false, 0, 7);
 	if (minb_env == 8) TAA_STREAM_GO(false, false, false, 0, 8);
 	if (minb_env == 5) TAA_STREAM_GO(false, false, false, 0, 5);
 	TAA_STREAM_GO(false, false, false, 0, 6);

@@ -449,3 +449,65 @@ def test_4k_eight_frames_free_running(oracle):
     q = 99.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
     assert q >= PSNR_MIN, f"PSNR after 8 free-running 4K frames: {q:.1f} dB"
     tuned.close(); exact.close()
+
+
+def test_band_peers_on_one_gpu():
+    """taa_band_peers without a second GPU: two band contexts of one frame in ONE process, each registered as the other's neighbour (plain device
+    pointers instead of IPC mappings), driven on two CUDA streams with no synchronisation between them. The resolve kernel stores each band's
+    boundary rows into the other band's halo and the flags order the frames. After 7 frames both bands — halo rows included — equal the
+    whole-frame resolve bit for bit (motion that is not a whole number of texels)."""
+    import ctypes as C
+    w, h, halo = 1920, 1080, 20
+    dev = torch.device("cuda")
+    lib = abi.load_library()
+    sc = SyntheticScene(w, h, device=dev, with_aux=False, pan_px=(3.25, 7.5), mover_px=(-6.5, 5.25))
+    p = configs.config2_resolve()
+    bands = [(0, h // 2), (h // 2, h - h // 2)]
+    hy = [(max(0, a - halo), min(h, a + n + halo)) for a, n in bands]
+    hist = [[torch.zeros(b - a, w, 4, dtype=torch.float16, device=dev) for _ in range(2)] for a, b in hy]
+    flags = [torch.zeros(abi.TAA_BAND_FLAG_WORDS, dtype=torch.int32, device=dev) for _ in bands]
+    res = [torch.zeros(n, w, 4, dtype=torch.float16, device=dev) for _, n in bands]
+    ctxs = [host.TaaContext((w, h), band=b) for b in bands]
+    streams = [torch.cuda.Stream() for _ in bands]
+    torch.cuda.synchronize()
+    for r in range(2):
+        o = 1 - r
+        pb = abi.taa_band_peer()
+        pb.history[0], pb.history[1] = hist[o][0].data_ptr(), hist[o][1].data_ptr()
+        pb.row_pitch, pb.y0, pb.band_rows, pb.flags = w * 8, hy[o][0], bands[o][1], flags[o].data_ptr()
+        up, dn = (C.byref(pb), None) if r == 1 else (None, C.byref(pb))  # band 1's neighbour lies above it, band 0's below
+        st = lib.taa_band_peers(ctxs[r]._h, up, dn, hist[r][0].data_ptr(), hist[r][1].data_ptr(), flags[r].data_ptr(), halo)
+        assert st == abi.TAA_OK, lib.taa_last_error_string(ctxs[r]._h).decode()
+    whole = host.TaaContext((w, h))
+    wh = [torch.zeros(h, w, 4, dtype=torch.float16, device=dev) for _ in range(2)]
+    wres = torch.zeros(h, w, 4, dtype=torch.float16, device=dev)
+    nframes = 7
+    frames = [sc.frame(n) for n in range(nframes)]
+    torch.cuda.synchronize()
+    for n, f in enumerate(frames):
+        u = configs.uniforms_for(p, f.jitter_ndc, reset_history=(n == 0))
+        whole.resolve(u, color=f.color, depth=f.depth, velocity=f.velocity, history_in=wh[n & 1], history_out=wh[1 - (n & 1)], result=wres)
+    torch.cuda.synchronize()
+    for n, f in enumerate(frames):  # both bands enqueue all their frames; only the flags order them against each other
+        u = configs.uniforms_for(p, f.jitter_ndc, reset_history=(n == 0))
+        for r in (1, 0):
+            a, cnt = bands[r]
+            i0, i1 = max(0, a - 2), min(h, a + cnt + 2)
+            with torch.cuda.stream(streams[r]):
+                ctxs[r].resolve(u, stream=streams[r], color=(f.color[i0:i1], i0), depth=(f.depth[i0:i1], i0), velocity=(f.velocity[i0:i1], i0),
+                                history_in=(hist[r][n & 1], hy[r][0]), history_out=(hist[r][1 - (n & 1)], hy[r][0]), result=(res[r], a))
+    torch.cuda.synchronize()
+    last = 1 - ((nframes - 1) & 1)
+    for r in range(2):
+        assert ctxs[r].poll_status(streams[r]) == abi.TAA_OK, lib.taa_last_error_string(ctxs[r]._h).decode()
+        a, cnt = bands[r]
+        assert torch.equal(hist[r][last].view(torch.int16), wh[last][hy[r][0]:hy[r][1]].view(torch.int16)), f"band {r}: history (band + halo rows) differs from the whole frame"
+        assert torch.equal(res[r].view(torch.int16), wres[a:a + cnt].view(torch.int16)), f"band {r}: result differs from the whole frame"
+    # a call the streaming kernel cannot serve alone is refused on such a context
+    with pytest.raises(abi.TaaError):
+        m = torch.zeros(bands[0][1], w, dtype=torch.int32, device=dev)
+        f = frames[0]
+        ctxs[0].resolve(configs.uniforms_for(p, f.jitter_ndc), color=(f.color[0:bands[0][1] + 2], 0), depth=(f.depth[0:bands[0][1] + 2], 0),
+                        velocity=(f.velocity[0:bands[0][1] + 2], 0), history_in=(hist[0][0], 0), history_out=(hist[0][1], 0), mask=(m, 0))
+    for c in ctxs + [whole]:
+        c.close()
