@@ -14,6 +14,17 @@ p = configs.config2_resolve()
 ctx = host.TaaContext((W, H), band=(y0, y1 - y0))
 hist = [torch.zeros(hy1 - hy0, W, 4, dtype=torch.float16, device=dev) for _ in range(2)]
 res = torch.zeros(y1 - y0, W, 4, dtype=torch.float16, device=dev)
+if os.environ.get("PEER") == "1":
+    # the band as its own neighbour on both sides (a torus): the PEER kernel variant with its dispatch order, second stores, waits and signals,
+    # minus the NVLink hop — what the variant costs by itself
+    import ctypes as C
+    lib = abi.load_library()
+    flags = torch.zeros(abi.TAA_BAND_FLAG_WORDS, dtype=torch.int32, device=dev)
+    pb = abi.taa_band_peer()
+    pb.history[0], pb.history[1] = hist[0].data_ptr(), hist[1].data_ptr()
+    pb.row_pitch, pb.y0, pb.band_rows, pb.flags = W * 8, hy0, y1 - y0, flags.data_ptr()
+    st = lib.taa_band_peers(ctx._h, C.byref(pb), C.byref(pb), hist[0].data_ptr(), hist[1].data_ptr(), flags.data_ptr(), halo)
+    assert st == 0, lib.taa_last_error_string(ctx._h).decode()
 stream = torch.cuda.Stream()
 prep = []
 for n in range(4):
@@ -28,4 +39,4 @@ torch.cuda.synchronize()
 run(8); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(stream); run(200); e1.record(stream); torch.cuda.synchronize()
-print("band %dx%d of %dx%d: ms per frame %.5f  (R=%s tail=%s rs=%s hints=%s)" % (W, y1 - y0, W, H, e0.elapsed_time(e1) / 200, os.environ.get("TAA_STREAM_R"), os.environ.get("TAA_STREAM_TAIL"), os.environ.get("TAA_STREAM_RS"), os.environ.get("TAA_STREAM_HINTS")))
+print("band %dx%d of %dx%d: ms per frame %.5f  (peer=%s R=%s tail=%s rs=%s hints=%s) status %d" % (W, y1 - y0, W, H, e0.elapsed_time(e1) / 200, os.environ.get("PEER"), os.environ.get("TAA_STREAM_R"), os.environ.get("TAA_STREAM_TAIL"), os.environ.get("TAA_STREAM_RS"), os.environ.get("TAA_STREAM_HINTS"), ctx.poll_status(stream)))

@@ -28,6 +28,27 @@ def band_of(height: int, world: int, rank: int):
     return rank * height // world, (rank + 1) * height // world
 
 
+def balanced_bounds(bounds, times, quantum: int = 2, min_rows: int = 1):
+    """Row boundaries that equalise the bands' cost, given the time each band took with the boundaries `bounds` (cost taken as uniform
+    inside a band): the cumulative cost is cut into equal parts. Boundaries are multiples of `quantum`, every band keeps >= min_rows rows."""
+    world = len(times)
+    dens = [t / max(1, bounds[r + 1] - bounds[r]) for r, t in enumerate(times)]
+    total = sum(times)
+    out = [bounds[0]]
+    r, acc = 0, 0.0  # acc: cost of the bands before band r
+    for k in range(1, world):
+        target = total * k / world
+        while r < world - 1 and acc + times[r] < target:
+            acc += times[r]
+            r += 1
+        y = bounds[r] + (target - acc) / dens[r] if dens[r] > 0 else bounds[r + 1]
+        y = int(round(y / quantum)) * quantum
+        y = max(out[-1] + min_rows, min(y, bounds[-1] - (world - k) * min_rows))
+        out.append(y)
+    out.append(bounds[-1])
+    return out
+
+
 @dataclass
 class BandLayout:
     height: int
@@ -35,12 +56,18 @@ class BandLayout:
     rank: int
     halo: int        # history rows kept above/below the band
     apron: int = 2   # input rows kept above/below the band (3x3 neighbourhood + velocity taps + sampler bleed)
+    bounds: Optional[list] = None  # world + 1 row boundaries (default: equal bands)
+
+    def band(self, r: int):
+        return (self.bounds[r], self.bounds[r + 1]) if self.bounds is not None else band_of(self.height, self.world, r)
 
     def __post_init__(self):
-        self.y0, self.y1 = band_of(self.height, self.world, self.rank)
+        if self.bounds is not None:
+            assert len(self.bounds) == self.world + 1 and self.bounds[0] == 0 and self.bounds[-1] == self.height and all(b > a for a, b in zip(self.bounds, self.bounds[1:]))
+        self.y0, self.y1 = self.band(self.rank)
         self.hy0, self.hy1 = max(0, self.y0 - self.halo), min(self.height, self.y1 + self.halo)
         self.iy0, self.iy1 = max(0, self.y0 - self.apron), min(self.height, self.y1 + self.apron)
-        smallest = min(b - a for a, b in (band_of(self.height, self.world, r) for r in range(self.world)))
+        smallest = min(b - a for a, b in (self.band(r) for r in range(self.world)))
         if self.world > 1 and smallest < self.halo:
             raise ValueError(f"halo {self.halo} exceeds the smallest band ({smallest} rows): use fewer ranks or replicate=True")
 
@@ -80,7 +107,7 @@ class HaloExchanger:
 
 def gather_full_history(band: torch.Tensor, full: torch.Tensor, layout: BandLayout, group=None):
     """replicate=True: all-gather the bands of history_out into a full-frame buffer on every rank."""
-    sizes = [band_of(layout.height, layout.world, r) for r in range(layout.world)]
+    sizes = [layout.band(r) for r in range(layout.world)]
     if len({b - a for a, b in sizes}) == 1:
         dist.all_gather_into_tensor(full, band.contiguous(), group=group)
     else:
@@ -92,7 +119,7 @@ class ShardedTaa:
     """One rank's share of a row-band sharded resolve. Inputs for the band (plus apron) are produced locally."""
 
     def __init__(self, width: int, height: int, halo: int = 20, replicate: bool = False, flags: int = 0, device=None, group=None, apron: int = 2,
-                 exchange: str = "nccl"):
+                 exchange: str = "nccl", bounds=None):
         """exchange = "nccl": the boundary strips are resolved by their own launches and sent / received (works for every settings block);
         "peer": ONE launch per band and frame, the resolve kernel stores the boundary rows into the neighbours' halos itself and the next frame's
         boundary units wait on a flag (taa_band_peers; calls the streaming kernel serves alone, i.e. the config 2 family)."""
@@ -100,7 +127,7 @@ class ShardedTaa:
         assert exchange in ("nccl", "peer")
         self.W, self.H = width, height
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.L = BandLayout(height, self.world, self.rank, halo, apron)
+        self.L = BandLayout(height, self.world, self.rank, halo, apron, bounds)
         self.replicate = replicate
         self.group = group
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -401,6 +428,34 @@ def _whole_frame_reference(W, H, p, flags, dev, cfg_id, sh, halo, replicate):
     return ms, same, ndiff, maxd
 
 
+def _band_alone_ms(W, H, p, flags, dev, cfg_id, y0, y1, halo, apron, frames_n: int = 24):
+    """Device time per frame of rows [y0, y1) resolved on this GPU alone (no neighbours, no exchange): what the band's content costs."""
+    from . import configs, host
+    from .synth import SyntheticScene
+    hy0, hy1, iy0, iy1 = max(0, y0 - halo), min(H, y1 + halo), max(0, y0 - apron), min(H, y1 + apron)
+    sc = SyntheticScene(W, H, device=dev, with_aux=False, rows=(iy0, iy1))
+    f = [sc.frame(0), sc.frame(1)]
+    ctx = host.TaaContext((W, H), band=(y0, y1 - y0), flags=flags)
+    hist = [torch.zeros(hy1 - hy0, W, 4, dtype=torch.float16, device=dev) for _ in range(2)]
+    res = torch.zeros(y1 - y0, W, 4, dtype=torch.float16, device=dev)
+    u = [configs.uniforms_for(p, x.jitter_ndc) for x in f]
+    stream = torch.cuda.Stream(device=dev)
+    prep = [ctx.images(color=(f[k].color, iy0), depth=(f[k].depth, iy0), velocity=(f[k].velocity, iy0), history_in=(hist[k], hy0), history_out=(hist[1 - k], hy0),
+                       result=(res, y0), history_depth=(f[1 - k].depth, iy0) if cfg_id == 3 else None) for k in range(2)]
+    torch.cuda.synchronize()
+    for k in range(6):
+        ctx.resolve_prepared(prep[k & 1], u[k & 1], stream.cuda_stream)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for k in range(frames_n):
+        ctx.resolve_prepared(prep[k & 1], u[k & 1], stream.cuda_stream)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / frames_n
+    ctx.close()
+    return ms
+
+
 # ---- bench (N > 1) ------------------------------------------------------------------------------------------------------------------
 def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
     from . import abi, configs
@@ -422,7 +477,21 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
     # config 2 (the streaming kernel alone): boundary rows stored into the neighbours' halos by the kernel, one launch per band and frame;
     # config 3 / the exact kernel (a fix-up or general launch rewrites pixels): boundary strips + NCCL send/recv. TAA_SHARDED_EXCHANGE overrides.
     exchange = os.environ.get("TAA_SHARDED_EXCHANGE", "peer" if (cfg_id == 2 and not args.exact and not replicate) else "nccl")
-    sh = ShardedTaa(W, H, halo=halo, replicate=replicate, flags=flags, device=dev, apron=halo if cfg_id == 3 else 2, exchange=exchange)
+    apron = halo if cfg_id == 3 else 2
+    # Optional (TAA_SHARDED_BALANCE=1): band heights that follow the content's cost — every rank times its band alone, the cumulative cost is
+    # cut into equal parts, twice. Measured on 4 x B200 (8K, the bench scene): rows [1130, 1002, 1048, 1140], 0.1121 ms against 0.1109 with
+    # equal bands: the ranks run in lockstep and the step time is not set by the content of the slowest band, so equal bands stay the default.
+    bounds, balance_note = None, "equal bands"
+    if world > 1 and not replicate and os.environ.get("TAA_SHARDED_BALANCE", "0") == "1":
+        bounds = [r * H // world for r in range(world + 1)]
+        for _ in range(2):
+            t = torch.tensor([_band_alone_ms(W, H, p, flags, dev, cfg_id, bounds[rank], bounds[rank + 1], halo, apron)], device=dev)
+            ts = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(ts, t)
+            times = [float(x.item()) for x in ts]
+            bounds = balanced_bounds(bounds, times, quantum=2, min_rows=max(3 * halo, 64))
+        balance_note = f"band heights follow the measured cost of the content (each band timed alone, two rounds): rows {[b - a for a, b in zip(bounds, bounds[1:])]}"
+    sh = ShardedTaa(W, H, halo=halo, replicate=replicate, flags=flags, device=dev, apron=apron, exchange=exchange, bounds=bounds)
     L = sh.L
     NSETS = 4
     # ---- before anything is timed: the same two frames on ONE GPU (every rank does it for itself), (a) as the strong-scaling reference
@@ -586,7 +655,7 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
             "fps": round(1e3 / ms_per_step, 1),
             "config": {"workload": f"{W}x{H} TAA resolve sharded in {world} row bands, BASELINE configs[3] (config {cfg_id} settings)",
                        "arithmetic": "exact general kernel" if args.exact else ("tuned kernels + exact fix-up pass" if cfg_id == 3 else "tuned kernels alone (no mask bound: nothing for the exact fix-up pass to decide)"),
-                       "halo_rows": halo,
+                       "halo_rows": halo, "bands": balance_note,
                        "exchange": ("all-gather of the history bands (replicated history: correct for unbounded motion)" if replicate else
                                     "peer stores: the resolve kernel writes its first / last halo rows into the neighbours' halos over NVLink and signals a flag; "
                                     "the neighbours' boundary units of the next frame wait on it (taa_band_peers) - one launch per band and frame, no collective" if sh.peer else
