@@ -370,13 +370,7 @@ __device__ __forceinline__ unsigned int smid() { unsigned int t; asm volatile("m
 
 // How a launch cuts its band into units: row blocks 0 .. nbig - 1 are R rows high, the blocks after them Rs (<= R) rows: the CTAs are dispatched in
 // index order, so the last wave consists of short units and the launch ends on a finer grain (decreasing chunk sizes, as in guided self-scheduling).
-// With a neighbour below, the short blocks lie ABOVE the band's last nlast blocks (R rows again): the bottom boundary blocks are dispatched first
-// (peer mode), and the units that are dispatched last should still be the short ones.
-struct UnitGeo { int nx, R, nbig, Rs, nshort, nlast, ny, nbt, nbb; };  // ny = nbig + nshort + nlast row blocks; the first nbt / last nbb of them are the band's boundary blocks (peer mode)
-__host__ __device__ __forceinline__ int geo_row(const UnitGeo& g, int b) {  // first row of row block b, relative to the band
-	return b < g.nbig ? b * g.R : b < g.nbig + g.nshort ? g.nbig * g.R + (b - g.nbig) * g.Rs : g.nbig * g.R + g.nshort * g.Rs + (b - g.nbig - g.nshort) * g.R;
-}
-__host__ __device__ __forceinline__ int geo_rows(const UnitGeo& g, int b) { return (b < g.nbig || b >= g.nbig + g.nshort) ? g.R : g.Rs; }
+struct UnitGeo { int nx, R, nbig, Rs, ny, nbt, nbb; };  // ny row blocks; the first nbt / last nbb of them are the band's boundary blocks (peer mode)
 
 // ---- row bands without a per-frame collective (PEER variants) ------------------------------------------------------------------------------
 // A band's first / last `halo` rows of history_out are what the neighbour above / below reads as the halo of its history_in in the next frame.
@@ -454,8 +448,8 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	const int strip = bx * NWARP + warp;
 	// rows this unit owns (writes); with a sharpening epilogue it also resolves the row above and the row below them, whose values the
 	// plus-shaped stencil needs (whole frames only: the follow-on passes do not run on bands)
-	const int Yo = A.band_y0 + geo_row(geo, by);
-	const int no = min(geo_rows(geo, by), A.band_y0 + A.band_rows - Yo);
+	const int Yo = A.band_y0 + (by < geo.nbig ? by * geo.R : geo.nbig * geo.R + (by - geo.nbig) * geo.Rs);
+	const int no = min(by < geo.nbig ? geo.R : geo.Rs, A.band_y0 + A.band_rows - Yo);
 	const int Y0 = EPI ? max(Yo - 1, 0) : Yo;
 	const int nr = EPI ? min(Yo + no, H - 1) - Y0 + 1 : no;
 	constexpr int STEP_X = EPI ? OWS - 2 : OWS;
@@ -752,6 +746,13 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	auto store_row = [&](const PixOut& a, const PixOut& b, const int i) {
 		const bool own = !EPI || (Y0 + i >= Yo && Y0 + i < Yo + no);  // (the extra rows of the epilogue are resolved but not written)
 		store_px(A.history_out.p, o_hist, own ? p16h : 0u, own ? p0h : 0u, own ? p1h : 0u, a.rg, a.bh, b.rg, b.bh);
+		if (PEER) {  // the band's first / last halo rows go to the neighbour's halo as well
+			const int g = Y0 + i;
+			if (side_top && g < A.band_y0 + peer.halo)
+				store_px(peer.nb_hist[0], (unsigned int)(g - peer.nb_y0[0]) * (unsigned int)peer.nb_pitch[0] + (unsigned int)x0c * 8u, p16h, p0h, p1h, a.rg, a.bh, b.rg, b.bh);
+			if (side_bot && g >= A.band_y0 + A.band_rows - peer.halo)
+				store_px(peer.nb_hist[1], (unsigned int)(g - peer.nb_y0[1]) * (unsigned int)peer.nb_pitch[1] + (unsigned int)x0c * 8u, p16h, p0h, p1h, a.rg, a.bh, b.rg, b.bh);
+		}
 		store_px(A.result.p, o_res, own ? p16r : 0u, own ? p0r : 0u, own ? p1r : 0u, a.rg, a.br, b.rg, b.br);
 		if (EPI) {
 			const F3 nA = as_f3(a.rg, a.br), nB = as_f3(b.rg, b.br);
@@ -1076,20 +1077,6 @@ taa_resolve_stream_kernel(const __grid_constant__ ResolveArgs A, const __grid_co
 	}
 
 	if (PEER && (side_top || side_bot)) {
-		// The band's first / last halo rows go to the neighbour's halo as well. Not from the row loop (the predicated second stores cost every unit
-		// of the band ~5 % there): a boundary unit copies what it has just written — every lane the 16 bytes per row it stored itself.
-		for (int sd = 0; sd < 2; ++sd) {
-			if (!(sd == 0 ? side_top : side_bot)) continue;
-			const int ga = sd == 0 ? Y0 : max(Y0, A.band_y0 + A.band_rows - peer.halo);
-			const int gb = sd == 0 ? min(Y0 + nr, A.band_y0 + peer.halo) : Y0 + nr;
-			for (int g = ga; g < gb; ++g) {
-				const unsigned char* src = A.history_out.p + ((unsigned int)(g - A.history_out.y0) * (unsigned int)A.history_out.pitch + (unsigned int)x0c * 8u);
-				unsigned char* dst = peer.nb_hist[sd] + ((unsigned int)(g - peer.nb_y0[sd]) * (unsigned int)peer.nb_pitch[sd] + (unsigned int)x0c * 8u);
-				if (p16h) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
-				if (p0h) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
-				if (p1h) *reinterpret_cast<uint2*>(dst + 8) = *reinterpret_cast<const uint2*>(src + 8);
-			}
-		}
 		__threadfence_system();  // every lane's stores (local and peer) are ordered before the signal
 		__syncwarp();
 		if (lane == 0) {
@@ -1198,24 +1185,13 @@ UnitGeo unit_geometry(int nx, int band_rows, int resident, int rmax, bool hints_
 	UnitGeo geo;
 	geo.nx = nx; geo.R = R;
 	geo.Rs = rs_env >= 2 && rs_env <= R ? rs_env : max(2, (R / 2 + 1) & ~1);
-	// rows of the band: [nbig blocks of R | nshort blocks of Rs | nlast blocks of R]; only the band's very last block may be cut short
-	if (halo_bot > 0 && tail_pct > 0) {  // a neighbour below: its rows (at least halo_bot) come in blocks of R BEHIND the short blocks
-		geo.nshort = max(0, (int)((long long)band_rows * min(tail_pct, 100) / 100 + geo.Rs / 2) / geo.Rs);
-		while (geo.nshort > 0 && geo.nshort * geo.Rs + halo_bot > band_rows) --geo.nshort;
-		geo.nbig = max(0, (band_rows - halo_bot - geo.nshort * geo.Rs) / R);
-		const int last_rows = band_rows - geo.nbig * R - geo.nshort * geo.Rs;  // >= halo_bot
-		geo.nlast = (last_rows + R - 1) / R;
-	} else {
-		geo.nlast = 0;
-		geo.nbig = tail_pct > 0 ? (int)(((long long)band_rows * (100 - min(tail_pct, 100)) / 100) / R) : (band_rows + R - 1) / R;
-		const int rest = max(0, band_rows - geo.nbig * R);
-		geo.nshort = (rest + geo.Rs - 1) / geo.Rs;
-	}
-	geo.ny = geo.nbig + geo.nshort + geo.nlast;
+	geo.nbig = tail_pct > 0 ? (int)(((long long)band_rows * (100 - min(tail_pct, 100)) / 100) / R) : (band_rows + R - 1) / R;
+	const int rest = max(0, band_rows - geo.nbig * R);
+	geo.ny = geo.nbig + (rest + geo.Rs - 1) / geo.Rs;
 	geo.nbt = geo.nbb = 0;
 	for (int b = 0; b < geo.ny; ++b) {
-		const int y = geo_row(geo, b);
-		const int e = min(band_rows, y + geo_rows(geo, b));
+		const int y = b < geo.nbig ? b * R : geo.nbig * R + (b - geo.nbig) * geo.Rs;
+		const int e = min(band_rows, y + (b < geo.nbig ? R : geo.Rs));
 		if (halo_top > 0 && y < halo_top) ++geo.nbt;
 		if (halo_bot > 0 && e > band_rows - halo_bot) ++geo.nbb;
 	}
@@ -1262,13 +1238,12 @@ cudaError_t launch_variant(const ResolveArgs& A, const CUtensorMap& tmC, const C
 			pa.mine[sd] = (unsigned int)((sd == 0 ? geo.nbt : geo.nbb) * nstrips);
 		}
 		pa.flags = peers->flags; pa.halo = peers->halo; pa.q = peers->q; pa.wait = peers->wait;
-
 	}
 	const bool hinted = hints_on && (long long)nx * ny <= (long long)HINT_FLAGS;
 	const unsigned int* hin = hinted ? hints + (size_t)(hint_phase % 3) * HINT_WORDS : nullptr;
 	unsigned int* hout = hinted ? hints + (size_t)((hint_phase + 1) % 3) * HINT_WORDS : nullptr;
 	unsigned int* hclr = hinted ? hints + (size_t)((hint_phase + 2) % 3) * HINT_WORDS : nullptr;
-	const unsigned int sig = ((unsigned int)nx * 2654435761u) ^ ((unsigned int)ny * 40503u) ^ ((unsigned int)R << 24) ^ ((unsigned int)geo.Rs << 18) ^ ((unsigned int)geo.nbig * 977u) ^ ((unsigned int)geo.nlast * 7919u) ^ (unsigned int)A.band_y0 ^ ((unsigned int)A.out_w << 8) ^ 0x5eedu;
+	const unsigned int sig = ((unsigned int)nx * 2654435761u) ^ ((unsigned int)ny * 40503u) ^ ((unsigned int)R << 24) ^ ((unsigned int)geo.Rs << 18) ^ ((unsigned int)geo.nbig * 977u) ^ (unsigned int)A.band_y0 ^ ((unsigned int)A.out_w << 8) ^ 0x5eedu;
 	cfg.gridDim = dim3(nx * ny + (hinted ? (int)HINT_N : 0));
 	cfg.blockDim = dim3(32 * NWARP);
 	cfg.dynamicSmemBytes = smem;
