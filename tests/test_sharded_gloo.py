@@ -124,3 +124,27 @@ def test_band_layout_rules():
     assert BandLayout(4320, 8, 0, 20).hy0 == 0 and BandLayout(4320, 8, 7, 20).hy1 == 4320
     with pytest.raises(ValueError):
         BandLayout(64, 8, 0, 20)
+
+
+def test_balanced_bounds_and_uneven_layouts():
+    """Band boundaries that follow a measured cost (sharded.balanced_bounds) and the layout of uneven bands (pure host logic)."""
+    from taa_star_b200.sharded import BandLayout, balanced_bounds
+    H = 4320
+    eq = [r * H // 4 for r in range(5)]
+    assert balanced_bounds(eq, [1.0, 1.0, 1.0, 1.0]) == eq                      # equal cost: nothing moves
+    b = balanced_bounds(eq, [0.08, 0.11, 0.105, 0.08])
+    assert b[0] == 0 and b[-1] == H and all(y % 2 == 0 for y in b) and all(q > p for p, q in zip(b, b[1:]))
+    rows = [q - p for p, q in zip(b, b[1:])]
+    assert rows[1] < 1080 < rows[0] and rows[2] < 1080 < rows[3]                 # the expensive bands shrink, the cheap ones grow
+    # cost implied by the new boundaries under the same piecewise-constant density: equal within a few rows' worth
+    dens = [t / 1080 for t in (0.08, 0.11, 0.105, 0.08)]
+    def cost(a, c):
+        return sum(dens[k] * max(0, min(c, eq[k + 1]) - max(a, eq[k])) for k in range(4))
+    costs = [cost(p, q) for p, q in zip(b, b[1:])]
+    assert max(costs) - min(costs) < 3 * max(dens)
+    assert balanced_bounds([0, 10, 20], [1.0, 0.0], min_rows=2) == [0, 4, 20]   # every band keeps min_rows
+    for r in range(4):
+        L = BandLayout(H, 4, r, halo=20, apron=2, bounds=b)
+        assert (L.y0, L.y1) == (b[r], b[r + 1]) and L.hy0 == max(0, b[r] - 20) and L.hy1 == min(H, b[r + 1] + 20)
+    with pytest.raises(ValueError):
+        BandLayout(100, 2, 0, halo=20, bounds=[0, 90, 100])                      # a band lower than the halo
