@@ -1,20 +1,9 @@
 #!/bin/bash
-# quick GPU session: parity tests of the default path, kernel-only A/B lines
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-b() { timeout 300 python bench.py --kernel-only --steps 100 --warmup 6 "$@" 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['frac'], d['motion'])"; }
 {
-echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-echo "== pytest tuned+chain+streams"; timeout 1500 python -m pytest tests/test_tuned_gpu.py tests/test_chain_gpu.py tests/test_streams.py -m gpu -q --timeout=900 --tb=short 2>&1 | grep -E "^(FAILED|ERROR|E  )|passed|failed" | cut -c1-260 | head -30
-echo "-- pan persist"; b
-echo "-- pan persist off"; TAA_STREAM_PERSIST=0 b
-echo "-- varying persist"; b --motion varying
-echo "-- varying persist off"; TAA_STREAM_PERSIST=0 b --motion varying
-echo "-- pan persist tail 0"; TAA_STREAM_TAIL=0 b
-echo "-- pan persist tail 0 R 20"; TAA_STREAM_TAIL=0 TAA_STREAM_R=20 b
-echo "-- pan persist tail 0 R 16"; TAA_STREAM_TAIL=0 TAA_STREAM_R=16 b
-echo "-- pan persist R 20"; TAA_STREAM_R=20 b
-echo "== fused"; timeout 300 python scripts/debug/fused_time.py 2>&1 | tail -1
-echo "== fused persist off"; TAA_STREAM_PERSIST=0 timeout 300 python scripts/debug/fused_time.py 2>&1 | tail -1
+for r in 1 3; do
+for d in 0 64 0 64; do echo "dbg $d"; BANDS=8 RANK_ID=$r PEER=1 TAA_PEER_DEBUG=$d timeout 200 python scripts/debug/band_time.py 2>&1 | tail -1 | cut -c1-80; done
+done
 } > gpurun_out/quick.log 2>&1
 cat gpurun_out/quick.log
