@@ -271,7 +271,11 @@ TAA_API int taa_resolve_ex(taa_ctx* ctx, const taa_resolve_images* images, const
  * taa_frame — taa.comp plus the follow-on passes of render() (taa.hpp:1111-1159) in one call:
  * resolve -> [FXAA] -> [sharpen | CAS] -> [post-process]; `final` receives the image render() would blit to
  * the swapchain (taa.hpp:1161-1169). images->result may be NULL when a sharpener or post-process
- * consumes it (fused path keeps it on chip).
+ * consumes it. With a sharpener and an identity post-process (no zoom box, no splitter, no debug view) on the tuned
+ * settings family without a mask binding the whole chain is ONE launch: the sharpening pass is evaluated in the
+ * streaming resolve's epilogue on the resolved rows it still holds in registers, the unsharpened image is never
+ * written. Otherwise the resolve writes it (to images->result or an internal scratch image) and one follow-on
+ * launch evaluates [sharpen | CAS] + post-process together.
  */
 TAA_API int taa_frame(taa_ctx* ctx, const taa_resolve_images* images, const TaaUniforms* params,
                       const taa_post_chain* chain, const taa_image* final, void* stream);

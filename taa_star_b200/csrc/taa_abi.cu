@@ -192,6 +192,10 @@ int taa_create(taa_ctx** out_ctx, const taa_desc* desc) {
 	e = cudaMalloc(&c->d_status, sizeof(unsigned int));
 	if (e == cudaSuccess) e = cudaMemset(c->d_status, 0, sizeof(unsigned int));
 	if (e != cudaSuccess) { int r = cuda_fail(nullptr, e, "cudaMalloc(status)"); delete c; return r; }
+	// the streaming kernel's scheduling hints (allocated here, not at the first resolve: that call may be part of a stream capture, where an
+	// allocation is not allowed). A failure only costs the ordering hint.
+	if (cudaMalloc(&c->hints, stream_hint_bytes()) == cudaSuccess) cudaMemset(c->hints, 0, stream_hint_bytes());
+	else { c->hints = nullptr; cudaGetLastError(); }
 	*out_ctx = c;
 	return TAA_OK;
 }

@@ -55,10 +55,6 @@ cudaError_t dispatch_resolve(taa_ctx* c, const ResolveArgs& A, cudaStream_t s, i
 			c->fix_parity ^= 1;
 		}
 		const bool streaming = stream_supports(A);
-		if (streaming && !c->hints) {  // (a failed allocation only costs the ordering hint)
-			if (cudaMalloc(&c->hints, stream_hint_bytes()) == cudaSuccess) cudaMemsetAsync(c->hints, 0, stream_hint_bytes(), s);
-			else { c->hints = nullptr; cudaGetLastError(); }
-		}
 		StreamPeers sp, *peers = nullptr;
 		if (c->peers.on) {
 			// the boundary rows are stored into the neighbours' buffers by the resolve kernel itself: only a call that the streaming kernel serves alone

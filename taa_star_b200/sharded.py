@@ -476,7 +476,9 @@ def bench_main(args, ClockSampler, measured_peak, BYTES_PER_PX):
         halo = halo * W // 7680  # (the synthetic motion and the fix-up band scale with the frame: same angular motion, more pixels)
     # config 2 (the streaming kernel alone): boundary rows stored into the neighbours' halos by the kernel, one launch per band and frame;
     # config 3 / the exact kernel (a fix-up or general launch rewrites pixels): boundary strips + NCCL send/recv. TAA_SHARDED_EXCHANGE overrides.
-    exchange = os.environ.get("TAA_SHARDED_EXCHANGE", "peer" if (cfg_id == 2 and not args.exact and not replicate) else "nccl")
+    # (measured, 8K: 2 GPUs 0.187 ms over NCCL against 0.195 with peer stores — the three launches of the NCCL variant overlap consecutive frames;
+    # 4 GPUs 0.1215 against 0.1116; 8 GPUs 0.1071 against 0.0702)
+    exchange = os.environ.get("TAA_SHARDED_EXCHANGE", "peer" if (cfg_id == 2 and not args.exact and not replicate and world >= 3) else "nccl")
     apron = halo if cfg_id == 3 else 2
     # Optional (TAA_SHARDED_BALANCE=1): band heights that follow the content's cost — every rank times its band alone, the cumulative cost is
     # cut into equal parts, twice. Measured on 4 x B200 (8K, the bench scene): rows [1130, 1002, 1048, 1140], 0.1121 ms against 0.1109 with
