@@ -1,3 +1,4 @@
+"""taa_frame on a 4K frame with config 2 settings + [sharpen | CAS] + identity post-process: the one-launch fused chain (TAA_FUSED_CHAIN=0: resolve + streaming\nsharpening pass); SHARP=1|2 picks the sharpener, TAA_STREAM_EPI_MINB the register budget of the epilogue variant (tuning / ncu aid)."""
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 from taa_star_b200 import abi, configs, host
